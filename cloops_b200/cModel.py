@@ -1,0 +1,260 @@
+"""Drop-in for the scoring half of ``cLoops.cModel`` (cLoops/cModel.py:31-331).
+
+The permuted-local-background test needs, per candidate loop, 123 integers (ra, rb, rab, the sizes
+of 10+10 shifted windows and their 10x10 joint counts).  They are counted on the GPU by the batched
+range-count kernel (``cloops_range_counts``); the statistics on top of them are evaluated on the host
+with the SAME numpy/scipy calls the reference makes (cModel.py:114,148-160), so every float in the
+loop table is reproduced exactly.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import pandas as pd
+from scipy.stats import binom, hypergeom, poisson
+
+from . import device
+from .io import parseIv, parseJd
+
+
+class _Axis:
+    """One axis of the coverage model: what the reference keeps as ``[sorted coords, {coord: [rows]}]``
+    (cModel.py:31-42).  Held as the sorted coordinates plus the argsort permutation."""
+
+    def __init__(self, coords: np.ndarray):
+        self.order = np.argsort(coords, kind="stable")
+        self.keys = coords[self.order]
+
+    def rows(self, lo, hi) -> np.ndarray:
+        a = np.searchsorted(self.keys, lo, side="left")
+        b = np.searchsorted(self.keys, hi, side="right")
+        return self.order[a:b]
+
+
+class CoverageModel:
+    """Result of getGenomeCoverage.  ``model[0]`` / ``model[1]`` are the X / Y axes (host, lazy, for
+    getCounts); ``model.gpu`` is the resident device model the batched kernels use."""
+
+    def __init__(self, X: np.ndarray, Y: np.ndarray):
+        self.X = np.ascontiguousarray(X)
+        self.Y = np.ascontiguousarray(Y)
+        self.N = len(self.X)
+        self._axes = [None, None]
+        self._gpu = None
+
+    @property
+    def gpu(self) -> "device.Coverage":
+        if self._gpu is None:
+            self._gpu = device.Coverage(device.to_device_i32(self.X, "X"), device.to_device_i32(self.Y, "Y"))
+        return self._gpu
+
+    def __getitem__(self, k) -> _Axis:
+        if self._axes[k] is None:
+            self._axes[k] = _Axis(self.X if k == 0 else self.Y)
+        return self._axes[k]
+
+    def __len__(self):
+        return 2
+
+
+def getGenomeCoverage(f, cut=0):
+    """cModel.py:45-57: ``(model, N)``; ``(None, 0)`` when fewer than 2 PETs survive ``cut``."""
+    key, mat = parseJd(f, cut)
+    if mat.shape[0] < 2:
+        return None, 0
+    return CoverageModel(mat[:, 1], mat[:, 2]), mat.shape[0]
+
+
+def getCounts(iv, model):
+    """cModel.py:60-69: set of row indices whose coordinate lies in [iv[0], iv[1]] (inclusive)."""
+    return set(model.rows(iv[0], iv[1]).tolist())
+
+
+def getPETsforRegions(iva, ivb, model):
+    """cModel.py:72-80 -> (ra, rb, rab), counted on the GPU."""
+    r = model.gpu.region_pets([[iva[0], iva[1], ivb[0], ivb[1]]])[0]
+    return int(r[0]), int(r[1]), int(r[2])
+
+
+def getNearbyPairRegions(iva, ivb, win=5):
+    """cModel.py:83-105 with the reference's (py2) integer arithmetic."""
+    ca, cb = (iva[0] + iva[1]) // 2, (ivb[0] + ivb[1]) // 2
+    sa, sb = (iva[1] - iva[0]) // 2, (ivb[1] - ivb[0]) // 2
+    step = (sa + sb) // 2
+    shifts = [i for i in range(-win, win + 1) if i != 0]
+    ivas = [[max(0, ca + i * step - sa), max(0, ca + i * step + sa)] for i in shifts]
+    ivbs = [[max(0, cb + i * step - sb), max(0, cb + i * step + sb)] for i in shifts]
+    return ivas, ivbs
+
+
+def _stats(c: np.ndarray, N: int):
+    """cModel.py:113-114,128-161 on the 123 integers of one candidate."""
+    ra, rb, rab = int(c[0]), int(c[1]), int(c[2])
+    hyp = max([1e-300, hypergeom.sf(rab - 1.0, N, ra, rb)])
+    na = c[3:13].astype(np.float64)
+    nb = c[13:23].astype(np.int64)
+    joint = c[23:123].astype(np.float64).reshape(10, 10)
+    rabs = joint.reshape(-1)                                   # zeros stay in the list (:137,143)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        dens = joint / (na[:, None] * nb[None, :])
+    nbps = np.where(joint > 0, dens, 0.0).reshape(-1)
+    fdr = len(rabs[rabs > rab]) / float(len(rabs))
+    mrabs = float(np.mean(rabs))
+    if mrabs > 0:
+        es = rab / np.mean(rabs[rabs > 0])
+    else:
+        es = np.inf
+    pop = max([1e-300, poisson.sf(rab - 1.0, mrabs)])
+    bp = np.mean(nbps) * ra * rb / N
+    nbp = max([1e-300, binom.sf(rab - 1.0, N - rab, bp)])
+    return ra, rb, rab, es, fdr, hyp, pop, nbp
+
+
+def getMultiplePsFdr(iva, ivb, model, N, win=5):
+    """cModel.py:108-161 -> (ra, rb, rab, es, fdr, hyp, pop, nbp)."""
+    if win != 5:
+        raise ValueError("the GPU range-count kernel is built for win=5 (the only value the reference uses)")
+    c = model.gpu.range_counts([[iva[0], iva[1], ivb[0], ivb[1]]])[0]
+    return _stats(c, N)
+
+
+def getBonPvalues(ps):
+    """cModel.py:164-171."""
+    ps = np.array(ps)
+    ps = ps * len(ps)
+    ps[ps > 1.0] = 1.0
+    return ps
+
+
+def checkOneEndOverlap(xa, xb, ya, yb):
+    """cModel.py:174-182."""
+    if (ya <= xa <= yb) or (ya <= xb <= yb) or (ya <= xa <= xb <= yb):
+        return True
+    if (xa <= ya <= xb) or (xa <= yb <= xb) or (xa <= ya <= yb <= xb):
+        return True
+    return False
+
+
+def checkOverlap(ivai, ivbi, ivaj, ivbj):
+    """cModel.py:185-195."""
+    if ivai[0] != ivaj[0] or ivbi[0] != ivbj[0]:
+        return
+    return bool(checkOneEndOverlap(ivai[1], ivai[2], ivaj[1], ivaj[2])
+                and checkOneEndOverlap(ivbi[1], ivbi[2], ivbj[1], ivbj[2]))
+
+
+def _end_overlap(xa, xb, ya, yb):
+    """Vectorised checkOneEndOverlap: scalar (xa, xb) against arrays (ya, yb)."""
+    return (((ya <= xa) & (xa <= yb)) | ((ya <= xb) & (xb <= yb)) | ((xa <= ya) & (ya <= xb)) | ((xa <= yb) & (yb <= xb)))
+
+
+def removeDup(ds, bpcut=1e-5):
+    """cModel.py:198-259: greedy grouping of overlapping loops in key order (first member leads its
+    group), then per group keep the densest member among those with binomial p <= bpcut.  Same
+    grouping and the same winner as the reference; the inner loop runs vectorised over the pending
+    loops instead of pair by pair."""
+    keys = list(ds.keys())
+    n = len(keys)
+    if n == 0:
+        return {}
+    ivs = [(parseIv(ds[k]["iva"]), parseIv(ds[k]["ivb"])) for k in keys]
+    chrom_ids = {}
+    chrom = np.array([chrom_ids.setdefault((a[0], b[0]), len(chrom_ids)) for a, b in ivs])
+    a0 = np.array([a[1] for a, _ in ivs], dtype=np.int64)
+    a1 = np.array([a[2] for a, _ in ivs], dtype=np.int64)
+    b0 = np.array([b[1] for _, b in ivs], dtype=np.int64)
+    b1 = np.array([b[2] for _, b in ivs], dtype=np.int64)
+    taken = np.zeros(n, dtype=bool)
+    uniqueds = {}
+    groups = {}
+    for i in range(n - 1):
+        if taken[i]:
+            continue
+        j = np.arange(i + 1, n)
+        j = j[~taken[i + 1:]]
+        if len(j):
+            hit = (chrom[j] == chrom[i]) & _end_overlap(a0[i], a1[i], a0[j], a1[j]) & _end_overlap(b0[i], b1[i], b0[j], b1[j])
+            j = j[hit]
+        if len(j):
+            groups[i] = [i] + j.tolist()
+            taken[i] = True
+            taken[j] = True
+        else:
+            uniqueds[keys[i]] = ds[keys[i]]
+    for lead, members in groups.items():
+        ts = {}
+        for t in members:
+            d = ds[keys[t]]
+            if d["binomial_p-value"] > bpcut:
+                continue
+            ts[keys[t]] = float(d["rab"]) / d["ra"] / d["rb"]
+        if not ts:
+            continue
+        ts = pd.Series(ts)
+        ts.sort_values(inplace=True, ascending=False)
+        uniqueds[ts.index[0]] = ds[ts.index[0]]
+    return uniqueds
+
+
+def getIntSig(f, records, minPts, discut):
+    """cModel.py:262-331.  All candidates of the chromosome are counted in ONE batched kernel launch;
+    filtering (:284-291), key numbering (:280,292), de-duplication and Bonferroni follow the reference."""
+    print("Starting estimate significance for %s candidate interactions in %s" % (len(records), f))
+    model, N = getGenomeCoverage(f, discut)
+    print("Genomic coverage model built from %s" % f)
+    if N == 0:
+        print("No cis-PETs parsed as requiring distance cutoff >%s from %s" % (discut, f))
+        return None
+    cand = np.array([[max(0, r[1]), r[2], max(0, r[4]), r[5]] for r in records], dtype=np.int64).reshape(-1, 4)
+    counts = model.gpu.range_counts(cand) if len(cand) else np.zeros((0, 123), np.int32)
+    need = max(minPts)
+    ds = {}
+    i = 0
+    for k, r in enumerate(records):
+        chrom = r[0]
+        key = "%s-%s-%s" % (r[0], r[3], i)
+        iva = [int(cand[k, 0]), int(cand[k, 1])]
+        ivb = [int(cand[k, 2]), int(cand[k, 3])]
+        distance = abs(sum(ivb) / 2.0 - sum(iva) / 2.0)
+        if distance < discut:
+            continue
+        if counts[k, 2] < need:
+            continue
+        i += 1
+        ra, rb, rab, es, fdr, hyp, pop, nbp = _stats(counts[k], N)
+        ds[key] = {
+            "distance": distance, "ra": ra, "rb": rb, "rab": rab, "ES": es, "FDR": fdr,
+            "hypergeometric_p-value": hyp, "poisson_p-value": pop, "binomial_p-value": nbp,
+            "iva": "%s:%s-%s" % (chrom, iva[0], iva[1]), "ivb": "%s:%s-%s" % (chrom, ivb[0], ivb[1]),
+        }
+    del model
+    if len(ds) == 0:
+        return None
+    ds = removeDup(ds)
+    if len(ds) == 0:
+        return None
+    ds = removeDup(ds)
+    if len(ds) == 0:
+        return None
+    ds = pd.DataFrame(ds).T
+    ds["poisson_p-value_corrected"] = getBonPvalues(ds["poisson_p-value"])
+    ds["binomial_p-value_corrected"] = getBonPvalues(ds["binomial_p-value"])
+    ds["hypergeometric_p-value_corrected"] = getBonPvalues(ds["hypergeometric_p-value"])
+    return ds
+
+
+def markIntSig(ds, escut=2.0, fdrcut=1e-2, bpcut=1e-3, ppcut=1e-5, hypcut=1e-10):
+    """cModel.py:334-363 (ChIA-PET cut-offs)."""
+    ok = ((ds["ES"] >= escut) & (ds["FDR"] <= fdrcut) & (ds["hypergeometric_p-value"] <= hypcut)
+          & (ds["poisson_p-value"] <= ppcut) & (ds["binomial_p-value"] <= bpcut))
+    ds["significant"] = ok.astype(float).values
+    return ds
+
+
+def markIntSigHic(ds, escut=2.0, fdrcut=0.01, bpcut=1e-5, ppcut=1e-5):
+    """cModel.py:366-386 (HiChIP / Hi-C cut-offs: FDR strictly below, no hypergeometric test)."""
+    ok = ((ds["ES"] >= escut) & (ds["FDR"] < fdrcut) & (ds["poisson_p-value"] <= ppcut) & (ds["binomial_p-value"] <= bpcut))
+    ds["significant"] = ok.astype(float).values
+    return ds

@@ -1,0 +1,222 @@
+// Permuted-local-background range counting (cLoops/cModel.py:31-143).
+//
+// Coverage model (cModel.py:45-57): the chromosome's PETs sorted by X and, separately, by Y, so that
+// "X in [lo,hi]" and "Y in [lo,hi]" are contiguous slices (the reference's np.searchsorted, :65-66).
+// For a candidate (iva, ivb) the kernel evaluates the reference's set algebra as per-PET bit masks:
+//   in(W,p) = X_p in W  or  Y_p in W   (union of source and target hits, :73-78,:118-127)
+//   ra = #in(A), rb = #in(B), rab = #{X in A and Y in B}  (:72-80)
+//   na_i = #in(A_i), nb_j = #in(B_j), C_ij = #{in(A_i) and in(B_j)}  (:118-143), windows per :83-105.
+// Only PETs with X or Y inside the hull of all windows can contribute; each is visited exactly once
+// (X-sorted slice first, then the Y-sorted slice minus PETs already seen through X).
+#include <limits.h>
+
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+struct cloops_coverage {
+    int n = 0;
+    int* xs_x = nullptr;   // X-sorted: X
+    int* xs_y = nullptr;   //           partner Y
+    int* ys_y = nullptr;   // Y-sorted: Y
+    int* ys_x = nullptr;   //           partner X
+};
+
+namespace cloops {
+
+#define NW 11   // window 0 = the anchor itself, 1..10 = the shifted windows in the reference's order
+
+struct Windows {
+    int a0[NW], a1[NW], b0[NW], b1[NW];
+    int h0[2], h1[2];    // disjoint hull intervals
+    int nh;
+};
+
+__device__ __forceinline__ long long fdiv2(long long a) { return (a >= 0) ? a / 2 : -((-a + 1) / 2); }  // floor(a/2)
+
+__device__ void make_windows(int iva0, int iva1, int ivb0, int ivb1, int win, Windows& W) {
+    // cModel.py:89-104 (py2 integer division)
+    long long ca = fdiv2((long long)iva0 + iva1), cb = fdiv2((long long)ivb0 + ivb1);
+    long long sa = fdiv2((long long)iva1 - iva0), sb = fdiv2((long long)ivb1 - ivb0);
+    long long step = fdiv2(sa + sb);
+    W.a0[0] = iva0; W.a1[0] = iva1; W.b0[0] = ivb0; W.b1[0] = ivb1;
+    int k = 1;
+    for (int i = -win; i <= win; ++i) {
+        if (i == 0) continue;
+        long long v;
+        v = ca + i * step - sa; W.a0[k] = (int)max(0LL, min(v, (long long)INT_MAX));
+        v = ca + i * step + sa; W.a1[k] = (int)max(0LL, min(v, (long long)INT_MAX));
+        v = cb + i * step - sb; W.b0[k] = (int)max(0LL, min(v, (long long)INT_MAX));
+        v = cb + i * step + sb; W.b1[k] = (int)max(0LL, min(v, (long long)INT_MAX));
+        ++k;
+    }
+    const int nw = (win > 0) ? NW : 1;
+    int ha0 = INT_MAX, ha1 = INT_MIN, hb0 = INT_MAX, hb1 = INT_MIN;
+    for (int w = 0; w < nw; ++w) {
+        ha0 = min(ha0, W.a0[w]); ha1 = max(ha1, W.a1[w]);
+        hb0 = min(hb0, W.b0[w]); hb1 = max(hb1, W.b1[w]);
+    }
+    if (ha0 > hb0) { int t = ha0; ha0 = hb0; hb0 = t; t = ha1; ha1 = hb1; hb1 = t; }
+    if (hb0 <= ha1) { W.nh = 1; W.h0[0] = ha0; W.h1[0] = max(ha1, hb1); }
+    else { W.nh = 2; W.h0[0] = ha0; W.h1[0] = ha1; W.h0[1] = hb0; W.h1[1] = hb1; }
+}
+
+__device__ __forceinline__ int lower_bound_i(const int* __restrict__ a, int n, int v) {   // first idx with a[idx] >= v
+    int lo = 0, hi = n;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (__ldg(a + mid) < v) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+__device__ __forceinline__ int upper_bound_i(const int* __restrict__ a, int n, int v) {   // first idx with a[idx] > v
+    int lo = 0, hi = n;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (__ldg(a + mid) <= v) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+// one CTA per candidate.  out row: ra, rb, rab, na[10], nb[10], C[10][10]
+template <int WIN>
+__global__ void __launch_bounds__(128) range_count_kernel(const int* __restrict__ xs_x, const int* __restrict__ xs_y,
+                                                          const int* __restrict__ ys_y, const int* __restrict__ ys_x, int n,
+                                                          const int* __restrict__ cand, int* __restrict__ out) {
+    constexpr int NOUT = (WIN > 0) ? 123 : 3;
+    constexpr int NWIN = (WIN > 0) ? NW : 1;
+    __shared__ Windows W;
+    __shared__ int acc[NOUT];
+    __shared__ int seg[8];   // [h][0..1] = X-sorted slice, [h][2..3] = Y-sorted slice
+    const int m = blockIdx.x;
+    const int4 c = __ldg(reinterpret_cast<const int4*>(cand) + m);
+    for (int t = threadIdx.x; t < NOUT; t += blockDim.x) acc[t] = 0;
+    if (threadIdx.x == 0) make_windows(c.x, c.y, c.z, c.w, WIN, W);
+    __syncthreads();
+    if (threadIdx.x < 4 * W.nh) {
+        int h = threadIdx.x >> 2, which = threadIdx.x & 3;
+        int r;
+        if (which == 0) r = lower_bound_i(xs_x, n, W.h0[h]);
+        else if (which == 1) r = upper_bound_i(xs_x, n, W.h1[h]);
+        else if (which == 2) r = lower_bound_i(ys_y, n, W.h0[h]);
+        else r = upper_bound_i(ys_y, n, W.h1[h]);
+        seg[threadIdx.x] = r;
+    }
+    __syncthreads();
+    const int nh = W.nh;
+    for (int pass = 0; pass < 2 * nh; ++pass) {
+        const int h = pass >> 1, via_y = pass & 1;
+        const int lo = seg[4 * h + 2 * via_y], hi = seg[4 * h + 2 * via_y + 1];
+        for (int t = lo + threadIdx.x; t < hi; t += blockDim.x) {
+            int x, y;
+            if (!via_y) { x = __ldg(xs_x + t); y = __ldg(xs_y + t); }
+            else {
+                y = __ldg(ys_y + t); x = __ldg(ys_x + t);
+                bool seen = false;           // already visited through its X
+                for (int g = 0; g < nh; ++g) seen |= (x >= W.h0[g] && x <= W.h1[g]);
+                if (seen) continue;
+            }
+            unsigned ma = 0, mb = 0;
+#pragma unroll
+            for (int w = 0; w < NWIN; ++w) {
+                bool ina = (x >= W.a0[w] && x <= W.a1[w]) || (y >= W.a0[w] && y <= W.a1[w]);
+                bool inb = (x >= W.b0[w] && x <= W.b1[w]) || (y >= W.b0[w] && y <= W.b1[w]);
+                ma |= (ina ? 1u : 0u) << w;
+                mb |= (inb ? 1u : 0u) << w;
+            }
+            if ((ma | mb) == 0) continue;
+            if (ma & 1u) atomicAdd(&acc[0], 1);
+            if (mb & 1u) atomicAdd(&acc[1], 1);
+            if (x >= W.a0[0] && x <= W.a1[0] && y >= W.b0[0] && y <= W.b1[0]) atomicAdd(&acc[2], 1);
+            if (WIN > 0) {
+                unsigned wa = ma >> 1, wb = mb >> 1;
+                for (unsigned r = wa; r; r &= r - 1) atomicAdd(&acc[3 + (__ffs(r) - 1)], 1);
+                for (unsigned r = wb; r; r &= r - 1) atomicAdd(&acc[13 + (__ffs(r) - 1)], 1);
+                for (unsigned r = wa; r; r &= r - 1) {
+                    int i = __ffs(r) - 1;
+                    for (unsigned q = wb; q; q &= q - 1) atomicAdd(&acc[23 + 10 * i + (__ffs(q) - 1)], 1);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < NOUT; t += blockDim.x) out[(long long)m * NOUT + t] = acc[t];
+}
+
+__global__ void __launch_bounds__(256) iota_kernel(int* p, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = i;
+}
+
+}  // namespace cloops
+
+using namespace cloops;
+
+static int coverage_build(const int32_t* d_x, const int32_t* d_y, int64_t n, cloops_coverage** out, cudaStream_t st) {
+    if (n < 0 || n > 0x7fffff00LL) return fail(CLOOPS_EINVAL, "n=%lld out of range", (long long)n);
+    RET_IF(pool_init());
+    cloops_coverage* cov = new cloops_coverage();
+    *out = cov;
+    cov->n = (int)n;
+    if (n == 0) return 0;
+    CU_TRY(cudaMallocAsync((void**)&cov->xs_x, n * sizeof(int), st));
+    CU_TRY(cudaMallocAsync((void**)&cov->xs_y, n * sizeof(int), st));
+    CU_TRY(cudaMallocAsync((void**)&cov->ys_y, n * sizeof(int), st));
+    CU_TRY(cudaMallocAsync((void**)&cov->ys_x, n * sizeof(int), st));
+    Temp tmp(st);
+    size_t bytes = 0;
+    CU_TRY(cub::DeviceRadixSort::SortPairs(nullptr, bytes, d_x, cov->xs_x, d_y, cov->xs_y, (int)n, 0, 32, st));
+    void* d_tmp;
+    RET_IF(tmp.alloc((char**)&d_tmp, bytes));
+    CU_TRY(cub::DeviceRadixSort::SortPairs(d_tmp, bytes, d_x, cov->xs_x, d_y, cov->xs_y, (int)n, 0, 32, st));
+    CU_TRY(cub::DeviceRadixSort::SortPairs(d_tmp, bytes, d_y, cov->ys_y, d_x, cov->ys_x, (int)n, 0, 32, st));
+    return 0;
+}
+
+extern "C" {
+
+int cloops_coverage_build(const int32_t* d_x, const int32_t* d_y, int64_t n, cloops_coverage** out, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!out) return fail(CLOOPS_EINVAL, "out is NULL");
+    *out = nullptr;
+    stages_begin(st);
+    int rc = coverage_build(d_x, d_y, n, out, st);
+    if (rc != 0) {
+        cloops_coverage_free(*out);
+        *out = nullptr;
+        return rc;
+    }
+    stage_mark("coverage_sort", st);
+    return stages_end(st);
+}
+
+void cloops_coverage_free(cloops_coverage* cov) {
+    if (!cov) return;
+    if (cov->xs_x) cudaFreeAsync(cov->xs_x, 0);
+    if (cov->xs_y) cudaFreeAsync(cov->xs_y, 0);
+    if (cov->ys_y) cudaFreeAsync(cov->ys_y, 0);
+    if (cov->ys_x) cudaFreeAsync(cov->ys_x, 0);
+    delete cov;
+}
+
+int cloops_range_counts(const cloops_coverage* cov, const int32_t* d_cand, int64_t m, int32_t* d_out, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!cov) return fail(CLOOPS_EINVAL, "coverage is NULL");
+    if (m < 0 || m > 0x7fffffffLL) return fail(CLOOPS_EINVAL, "m out of range");
+    stages_begin(st);
+    if (m > 0) {
+        if (cov->n == 0) CU_TRY(cudaMemsetAsync(d_out, 0, (size_t)m * 123 * sizeof(int), st));
+        else LAUNCH(range_count_kernel<5>, (unsigned)m, 128, 0, st, cov->xs_x, cov->xs_y, cov->ys_y, cov->ys_x, cov->n, d_cand, d_out);
+    }
+    stage_mark("range_counts", st);
+    return stages_end(st);
+}
+
+int cloops_region_pets(const cloops_coverage* cov, const int32_t* d_cand, int64_t m, int32_t* d_out, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!cov) return fail(CLOOPS_EINVAL, "coverage is NULL");
+    if (m < 0 || m > 0x7fffffffLL) return fail(CLOOPS_EINVAL, "m out of range");
+    stages_begin(st);
+    if (m > 0) {
+        if (cov->n == 0) CU_TRY(cudaMemsetAsync(d_out, 0, (size_t)m * 3 * sizeof(int), st));
+        else LAUNCH(range_count_kernel<0>, (unsigned)m, 128, 0, st, cov->xs_x, cov->xs_y, cov->ys_y, cov->ys_x, cov->n, d_cand, d_out);
+    }
+    stage_mark("region_pets", st);
+    return stages_end(st);
+}
+
+}  // extern "C"

@@ -1,0 +1,425 @@
+// Labels of cDBSCAN (v1) and cDBSCAN2 (v2) over a built index, as order-free data-parallel rules.
+//
+// Both reference classes share the core set ( n(p) >= minPts, Manhattan, inclusive, self counted:
+// cDBSCAN.py:163-166,196-204 ; cDBSCAN2.py:333-334 ) and the components of the core graph; they differ
+// in cluster numbering, border ownership and survival:
+//   v1 (cDBSCAN.py:128-184): ids ascend with the smallest ROW of a core point of the component (its
+//       "seed"); a border point goes to the LARGEST id among clusters whose seed is within eps
+//       (:172-173 relabels every neighbour of a new seed), else to the SMALLEST adjacent id (:179-182);
+//       clusters that end with < minPts members are removed, ids keep their gaps (:149-152).
+//   v2 (cDBSCAN2.py:114-192): clusters are attempted in order of the first-inserted rotated cell that
+//       holds one of their core points (:117-140); a border point goes to the lowest-ranked ALIVE
+//       adjacent cluster (only label -1 points are ever collected); a cluster with < minPts members is
+//       released (:180-185) and its points fall to later clusters; ids are dense over survivors.
+#include <limits.h>
+
+#include <cub/cub.cuh>
+
+#include "index.cuh"
+
+namespace cloops {
+
+enum : unsigned char { ST_NONE = 0, ST_ALIVE = 1, ST_DEAD = 2, ST_UNDECIDED = 3 };
+
+struct Work {
+    int* cnt;        // [n_act] neighbour counts (saturated at minPts)
+    int* parent;     // [n_act] union-find over sorted indices (core points only)
+    int* rank;       // [n_act] per root: v1 = min row of core point ; v2 = min cell-first-row
+    int* ncore;      // [n_act] per root: core points
+    int* assigned;   // [n_act] root the point belongs to (or -1)
+    int* chead;      // [n_act] v2: sorted index of the first point of the point's rotated cell
+    int* cellmin;    // [n_act] v2: per cell head: smallest row in the cell
+    int* size;       // [n_act] v1: members per root ; v2: lb
+    int* ub;         // [n_act] v2: ub
+    unsigned char* status;  // [n_act] per root
+    int* flags;      // [n+1] rank-indexed survivor flags, then their exclusive scan
+    int* ids;        // [n+1]
+    int* list_und;   // [n_act] undecided roots
+    int* list_con;   // [n_act] contested border points
+    int* counters;   // [8]: 0 n_und, 1 n_con, 2 remaining, 3 n_dead, 4 n_comp, 5 n_core, 6 n_labelled
+};
+
+__global__ void __launch_bounds__(256) fill_int_kernel(int* p, int v, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// core flag into bit 63 of the key; union-find and per-root state initialised
+__global__ void __launch_bounds__(256) flag_kernel(u64* __restrict__ keys, GridParams P, int minPts, Work W, int want_cells) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n_act) return;
+    u64 k = keys[i] & KEY_MASK;
+    bool core = W.cnt[i] >= minPts;
+    keys[i] = core ? (k | CORE_FLAG) : k;
+    W.parent[i] = i;
+    W.rank[i] = INT_MAX;
+    W.ncore[i] = 0;
+    W.size[i] = 0;
+    W.status[i] = ST_NONE;
+    if (want_cells) {
+        // rotated floor cell = (strip, floor(u'/eps)) (cDBSCAN2.py:69-70); head = first sorted point of the cell
+        bool head = true;
+        if (i > 0) {
+            u64 kp = keys[i - 1] & KEY_MASK;   // flag bit of a neighbour may or may not be set yet: masked
+            u32 cu = ((u32)(k >> P.be) & P.umask) / (u32)P.eps;
+            u32 cup = ((u32)(kp >> P.be) & P.umask) / (u32)P.eps;
+            head = (k >> P.sshift) != (kp >> P.sshift) || cu != cup;
+        }
+        W.chead[i] = head ? i : 0;
+        W.cellmin[i] = INT_MAX;
+    }
+    if (core) atomicAdd(&W.counters[5], 1);
+}
+
+__global__ void __launch_bounds__(256) cellmin_kernel(const u32* __restrict__ rows, GridParams P, Work W) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n_act) return;
+    atomicMin(&W.cellmin[W.chead[i]], (int)rows[i]);
+}
+
+__device__ __forceinline__ int uf_find(int* parent, int x) {
+    int p = parent[x];
+    while (p != x) {
+        int g = parent[p];
+        if (g != p) parent[x] = g;    // path halving; always points at an ancestor
+        x = p;
+        p = g;
+    }
+    return x;
+}
+
+__device__ __forceinline__ void uf_union(int* parent, int a, int b) {
+    while (true) {
+        a = uf_find(parent, a);
+        b = uf_find(parent, b);
+        if (a == b) return;
+        if (a < b) { int t = a; a = b; b = t; }        // hook the larger root under the smaller
+        int old = atomicCAS(&parent[a], a, b);
+        if (old == a) return;
+    }
+}
+
+// Core graph edges.  Every core-core edge joins points of the same strip or of adjacent strips.
+//  * same strip: core points within eps in u form chains; linking each core point to its nearest core
+//    point on the left (if within eps) connects every chain.
+//  * strip s-1: inside the u-window at most two chains of strip s-1 are visible; one union per chain
+//    (with any member that passes the v test) is enough.
+__global__ void __launch_bounds__(256) union_kernel(const u64* __restrict__ keys, const int* __restrict__ sstart, GridParams P,
+                                                    int* __restrict__ parent) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n_act) return;
+    const u64 key = keys[i];
+    if (!(key >> 63)) return;
+    const PointView p = view(key, P);
+    const int lo_s = __ldg(sstart + p.s + 1);
+    for (int j = i - 1; j >= lo_s; --j) {
+        u64 kq = keys[j];
+        if (((u32)(kq >> P.be) & P.umask) < p.ulo) break;
+        if (kq >> 63) { uf_union(parent, i, j); break; }
+    }
+    const int a = __ldg(sstart + p.s);
+    if (a < lo_s) {
+        u64 base = (u64)(p.s - 1) << P.bu;
+        int j = lower_bound_su(keys, a, lo_s, base | p.ulo, P.be);
+        u64 top = base | p.uhi;
+        long long last_core_u = -(1LL << 40);
+        bool linked = false;
+        for (; j < lo_s; ++j) {
+            u64 kq = keys[j];
+            if (key_su(kq, P.be) > top) break;
+            if (!(kq >> 63)) continue;
+            long long uq = (long long)((u32)(kq >> P.be) & P.umask);
+            if (uq - last_core_u > (long long)P.eps) linked = false;   // a new chain of strip s-1 starts
+            last_core_u = uq;
+            if (!linked && ((u32)kq & P.emask) >= p.vm) { uf_union(parent, i, j); linked = true; }
+        }
+    }
+}
+
+// full compression + per-component statistics
+__global__ void __launch_bounds__(256) compress_kernel(const u64* __restrict__ keys, const u32* __restrict__ rows, GridParams P,
+                                                       Work W, int variant) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n_act) return;
+    if (!(keys[i] >> 63)) { W.assigned[i] = -1; return; }
+    int r = uf_find(W.parent, i);
+    W.parent[i] = r;
+    W.assigned[i] = r;
+    atomicAdd(&W.ncore[r], 1);
+    int rk = (variant == CLOOPS_V1) ? (int)rows[i] : W.cellmin[W.chead[i]];
+    atomicMin(&W.rank[r], rk);
+    if (r == i) atomicAdd(&W.counters[4], 1);
+}
+
+// parent[] of core points may still be one hop short for points compressed before their root was
+// hooked?  No: unions finished in the previous kernel, so uf_find() returns final roots.  Kernels below
+// nevertheless resolve roots with root_of() which tolerates un-compressed parents.
+__device__ __forceinline__ int root_of(const int* parent, int x) {
+    int p = parent[x];
+    while (p != x) { x = p; p = parent[x]; }
+    return x;
+}
+
+// ---- v1 border ownership --------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) v1_border_kernel(const u64* __restrict__ keys, const int* __restrict__ sstart,
+                                                        const u32* __restrict__ rows, GridParams P, Work W) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n_act) return;
+    const u64 key = keys[i];
+    if (key >> 63) return;
+    const PointView p = view(key, P);
+    int best_seed_rank = -1, best_seed_root = -1, best_any_rank = INT_MAX, best_any_root = -1;
+    for_each_neighbour(keys, sstart, P, i, p, [&](int j, u64 kq) {
+        if (!(kq >> 63)) return true;
+        int r = root_of(W.parent, j);
+        int rk = W.rank[r];
+        if ((int)rows[j] == rk && rk > best_seed_rank) { best_seed_rank = rk; best_seed_root = r; }
+        if (rk < best_any_rank) { best_any_rank = rk; best_any_root = r; }
+        return true;
+    });
+    W.assigned[i] = best_seed_root >= 0 ? best_seed_root : best_any_root;
+}
+
+__global__ void __launch_bounds__(256) size_kernel(GridParams P, Work W) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n_act) return;
+    int a = W.assigned[i];
+    if (a >= 0) atomicAdd(&W.size[a], 1);
+}
+
+// ---- v2 survival ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) v2_status_kernel(const u64* __restrict__ keys, GridParams P, int minPts, Work W) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n_act) return;
+    if (!(keys[i] >> 63) || W.parent[i] != i) return;
+    if (W.ncore[i] >= minPts) {
+        W.status[i] = ST_ALIVE;
+    } else {
+        W.status[i] = ST_UNDECIDED;
+        W.list_und[atomicAdd(&W.counters[0], 1)] = i;
+    }
+}
+
+// border points adjacent to at least one undecided component
+__global__ void __launch_bounds__(256) v2_contested_kernel(const u64* __restrict__ keys, const int* __restrict__ sstart,
+                                                           GridParams P, Work W) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n_act) return;
+    const u64 key = keys[i];
+    if (key >> 63) return;
+    const PointView p = view(key, P);
+    bool hit = false;
+    for_each_neighbour(keys, sstart, P, i, p, [&](int j, u64 kq) {
+        if (!(kq >> 63)) return true;
+        if (W.status[root_of(W.parent, j)] == ST_UNDECIDED) { hit = true; return false; }
+        return true;
+    });
+    if (hit) W.list_con[atomicAdd(&W.counters[1], 1)] = i;
+}
+
+__global__ void __launch_bounds__(256) v2_reset_kernel(Work W, int n_und) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_und) return;
+    int r = W.list_und[t];
+    if (W.status[r] == ST_UNDECIDED) { W.size[r] = W.ncore[r]; W.ub[r] = W.ncore[r]; }
+    if (t == 0) W.counters[2] = 0;
+}
+
+// lb(K): border points for which K is the lowest-ranked non-dead adjacent component (K's for sure if K lives)
+// ub(K): border points adjacent to K with no decided-alive adjacent component of lower rank
+__global__ void __launch_bounds__(128) v2_accumulate_kernel(const u64* __restrict__ keys, const int* __restrict__ sstart,
+                                                            GridParams P, Work W, int n_con) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_con) return;
+    const int i = W.list_con[t];
+    const PointView p = view(keys[i], P);
+    int min_nd_rank = INT_MAX, min_nd_root = -1, min_alive_rank = INT_MAX;
+    for_each_neighbour(keys, sstart, P, i, p, [&](int j, u64 kq) {
+        if (!(kq >> 63)) return true;
+        int r = root_of(W.parent, j);
+        unsigned char st = W.status[r];
+        if (st == ST_DEAD) return true;
+        int rk = W.rank[r];
+        if (rk < min_nd_rank) { min_nd_rank = rk; min_nd_root = r; }
+        if (st == ST_ALIVE && rk < min_alive_rank) min_alive_rank = rk;
+        return true;
+    });
+    if (min_nd_root < 0) return;
+    if (W.status[min_nd_root] == ST_UNDECIDED) atomicAdd(&W.size[min_nd_root], 1);
+    // every distinct undecided adjacent component ranked below the best alive one
+    for_each_neighbour(keys, sstart, P, i, p, [&](int j, u64 kq) {
+        if (!(kq >> 63)) return true;
+        int r = root_of(W.parent, j);
+        if (W.status[r] != ST_UNDECIDED || W.rank[r] >= min_alive_rank) return true;
+        bool first = true;                      // count each component once: only at its first visit
+        for_each_neighbour(keys, sstart, P, i, p, [&](int j2, u64 kq2) {
+            if (j2 == j) return false;
+            if ((kq2 >> 63) && root_of(W.parent, j2) == r) { first = false; return false; }
+            return true;
+        });
+        if (first) atomicAdd(&W.ub[r], 1);
+        return true;
+    });
+}
+
+__global__ void __launch_bounds__(256) v2_decide_kernel(Work W, int n_und, int minPts) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_und) return;
+    int r = W.list_und[t];
+    if (W.status[r] != ST_UNDECIDED) return;
+    if (W.size[r] >= minPts) W.status[r] = ST_ALIVE;
+    else if (W.ub[r] < minPts) { W.status[r] = ST_DEAD; atomicAdd(&W.counters[3], 1); }
+    else atomicAdd(&W.counters[2], 1);
+}
+
+// final v2 ownership: lowest-ranked alive adjacent component (cDBSCAN2.py:130,162,352)
+__global__ void __launch_bounds__(256) v2_border_kernel(const u64* __restrict__ keys, const int* __restrict__ sstart,
+                                                        GridParams P, Work W) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n_act) return;
+    const u64 key = keys[i];
+    if (key >> 63) return;
+    const PointView p = view(key, P);
+    int best_rank = INT_MAX, best_root = -1;
+    for_each_neighbour(keys, sstart, P, i, p, [&](int j, u64 kq) {
+        if (!(kq >> 63)) return true;
+        int r = root_of(W.parent, j);
+        if (W.status[r] == ST_DEAD) return true;
+        int rk = W.rank[r];
+        if (rk < best_rank) { best_rank = rk; best_root = r; }
+        return true;
+    });
+    W.assigned[i] = best_root;
+}
+
+// ---- numbering ----------------------------------------------------------------------------------------
+// flags[rank of root] = 1 for every component that receives an id
+__global__ void __launch_bounds__(256) number_flags_kernel(const u64* __restrict__ keys, GridParams P, Work W, int variant) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n_act) return;
+    if (!(keys[i] >> 63) || W.parent[i] != i) return;
+    bool numbered = (variant == CLOOPS_V1) ? true : (W.status[i] != ST_DEAD);
+    if (numbered) W.flags[W.rank[i]] = 1;
+}
+
+__global__ void __launch_bounds__(256) label_kernel(const u32* __restrict__ rows, GridParams P, Work W, int variant, int minPts,
+                                                    int* __restrict__ labels) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n_act) return;
+    int a = W.assigned[i];
+    int lab = -1;
+    if (a >= 0) {
+        bool keep = (variant == CLOOPS_V1) ? (W.size[a] >= minPts) : (W.status[a] != ST_DEAD);
+        if (keep) lab = W.ids[W.rank[a]];
+    }
+    labels[rows[i]] = lab;
+    if (lab >= 0) atomicAdd(&W.counters[6], 1);
+}
+
+int index_dbscan(cloops_index* ix, int minPts, int variant, int* d_labels, int64_t* h_info, cudaStream_t st) {
+    const GridParams& P = ix->P;
+    if (minPts < 1) return fail(CLOOPS_EINVAL, "minPts must be >= 1 (got %d)", minPts);
+    if (variant != CLOOPS_V1 && variant != CLOOPS_V2) return fail(CLOOPS_EINVAL, "variant %d not served by the strip index", variant);
+    if (h_info) for (int k = 0; k < 8; ++k) h_info[k] = 0;
+    if (P.n == 0) return 0;
+    LAUNCH(fill_int_kernel, cdiv(P.n, 256), 256, 0, st, d_labels, -1, (long long)P.n);
+    if (P.n_act == 0) return 0;
+    const int na = P.n_act, g = cdiv(na, 256);
+    Temp tmp(st);
+    Work W;
+    RET_IF(tmp.alloc(&W.cnt, na));
+    RET_IF(tmp.alloc(&W.parent, na));
+    RET_IF(tmp.alloc(&W.rank, na));
+    RET_IF(tmp.alloc(&W.ncore, na));
+    RET_IF(tmp.alloc(&W.assigned, na));
+    RET_IF(tmp.alloc(&W.size, na));
+    RET_IF(tmp.alloc(&W.ub, na));
+    RET_IF(tmp.alloc(&W.status, na));
+    RET_IF(tmp.alloc(&W.flags, (size_t)P.n + 1));
+    RET_IF(tmp.alloc(&W.ids, (size_t)P.n + 1));
+    RET_IF(tmp.alloc(&W.counters, 8));
+    W.chead = W.cellmin = W.list_und = W.list_con = nullptr;
+    const bool v2 = variant == CLOOPS_V2;
+    if (v2) {
+        RET_IF(tmp.alloc(&W.chead, na));
+        RET_IF(tmp.alloc(&W.cellmin, na));
+        RET_IF(tmp.alloc(&W.list_und, na));
+        RET_IF(tmp.alloc(&W.list_con, na));
+    }
+    CU_TRY(cudaMemsetAsync(W.counters, 0, 8 * sizeof(int), st));
+    CU_TRY(cudaMemsetAsync(W.flags, 0, ((size_t)P.n + 1) * sizeof(int), st));
+
+    RET_IF(index_count(ix, minPts, W.cnt, st));
+    stage_mark("region_query", st);
+    LAUNCH(flag_kernel, g, 256, 0, st, ix->keys, P, minPts, W, v2 ? 1 : 0);
+    if (v2) {
+        size_t scan_bytes = 0;
+        CU_TRY(cub::DeviceScan::InclusiveScan(nullptr, scan_bytes, W.chead, W.chead, cub::Max(), na, st));
+        void* d_scan;
+        RET_IF(tmp.alloc((char**)&d_scan, scan_bytes));
+        CU_TRY(cub::DeviceScan::InclusiveScan(d_scan, scan_bytes, W.chead, W.chead, cub::Max(), na, st));
+        LAUNCH(cellmin_kernel, g, 256, 0, st, ix->rows, P, W);
+    }
+    stage_mark("flags_cells", st);
+    LAUNCH(union_kernel, g, 256, 0, st, ix->keys, ix->sstart, P, W.parent);
+    stage_mark("union", st);
+    LAUNCH(compress_kernel, g, 256, 0, st, ix->keys, ix->rows, P, W, variant);
+    stage_mark("compress", st);
+
+    int counters[8] = {0};
+    if (!v2) {
+        LAUNCH(v1_border_kernel, g, 256, 0, st, ix->keys, ix->sstart, ix->rows, P, W);
+        LAUNCH(size_kernel, g, 256, 0, st, P, W);
+        stage_mark("border", st);
+    } else {
+        LAUNCH(v2_status_kernel, g, 256, 0, st, ix->keys, P, minPts, W);
+        CU_TRY(cudaMemcpyAsync(counters, W.counters, sizeof(counters), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        int n_und = counters[0];
+        if (n_und > 0) {
+            LAUNCH(v2_contested_kernel, g, 256, 0, st, ix->keys, ix->sstart, P, W);
+            CU_TRY(cudaMemcpyAsync(counters, W.counters, sizeof(counters), cudaMemcpyDeviceToHost, st));
+            CU_TRY(cudaStreamSynchronize(st));
+            int n_con = counters[1];
+            for (int round = 0;; ++round) {
+                LAUNCH(v2_reset_kernel, cdiv(n_und, 256), 256, 0, st, W, n_und);
+                if (n_con > 0) LAUNCH(v2_accumulate_kernel, cdiv(n_con, 128), 128, 0, st, ix->keys, ix->sstart, P, W, n_con);
+                LAUNCH(v2_decide_kernel, cdiv(n_und, 256), 256, 0, st, W, n_und, minPts);
+                CU_TRY(cudaMemcpyAsync(counters, W.counters, sizeof(counters), cudaMemcpyDeviceToHost, st));
+                CU_TRY(cudaStreamSynchronize(st));
+                if (counters[2] == 0) break;
+                if (round > na) return fail(CLOOPS_ECUDA, "v2 survival did not converge");
+            }
+        }
+        stage_mark("survival", st);
+        LAUNCH(v2_border_kernel, g, 256, 0, st, ix->keys, ix->sstart, P, W);
+        stage_mark("border", st);
+    }
+    LAUNCH(number_flags_kernel, g, 256, 0, st, ix->keys, P, W, variant);
+    {
+        size_t scan_bytes = 0;
+        CU_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, W.flags, W.ids, P.n + 1, st));
+        void* d_scan;
+        RET_IF(tmp.alloc((char**)&d_scan, scan_bytes));
+        CU_TRY(cub::DeviceScan::ExclusiveSum(d_scan, scan_bytes, W.flags, W.ids, P.n + 1, st));
+    }
+    LAUNCH(label_kernel, g, 256, 0, st, ix->rows, P, W, variant, minPts, d_labels);
+    stage_mark("labels", st);
+    if (h_info) {
+        int n_clusters = 0;
+        CU_TRY(cudaMemcpyAsync(counters, W.counters, sizeof(counters), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaMemcpyAsync(&n_clusters, W.ids + P.n, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        h_info[0] = P.n_act;
+        h_info[1] = n_clusters;
+        h_info[2] = counters[4];
+        h_info[3] = counters[5];
+        h_info[4] = counters[3];
+        h_info[5] = P.ns;
+        h_info[6] = P.be + P.bu + P.bs;
+        h_info[7] = counters[6];
+    }
+    return 0;
+}
+
+}  // namespace cloops

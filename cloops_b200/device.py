@@ -1,0 +1,155 @@
+"""Device-side plumbing (torch tensors as HBM buffers + the caller's CUDA stream) around the C ABI."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import CloopsError, check
+
+COORD_LIMIT = 1 << 30
+
+
+def require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise CloopsError("cloops_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def to_device_i32(a, name="array") -> torch.Tensor:
+    """numpy / torch integer array -> contiguous int32 CUDA tensor (range-checked)."""
+    dev = require_cuda()
+    if isinstance(a, torch.Tensor):
+        if a.is_cuda and a.dtype == torch.int32 and a.is_contiguous():
+            return a
+        if a.dtype != torch.int32:
+            if a.numel() and (int(a.min()) < -COORD_LIMIT or int(a.max()) >= COORD_LIMIT):
+                raise CloopsError("%s: coordinates must lie in [-2^30, 2^30)" % name)
+            a = a.to(torch.int32)
+        return a.contiguous().to(dev, non_blocking=True)
+    a = np.asarray(a)
+    if a.dtype != np.int32:
+        if a.size and (a.min() < -COORD_LIMIT or a.max() >= COORD_LIMIT):
+            raise CloopsError("%s: coordinates must lie in [-2^30, 2^30)" % name)
+        a = a.astype(np.int32)
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=True)
+
+
+def dbscan_device(dx: torch.Tensor, dy: torch.Tensor, eps: int, minPts: int, variant: int, cut: int = 0):
+    """Labels (int32 CUDA tensor, row order, -1 = noise) + info dict, everything resident in HBM."""
+    n = dx.numel()
+    labels = torch.empty(n, dtype=torch.int32, device=dx.device)
+    info = (C.c_int64 * 8)()
+    check(_lib.lib().cloops_dbscan(dx.data_ptr(), dy.data_ptr(), n, int(eps), int(minPts), int(cut), int(variant),
+                                   labels.data_ptr(), C.addressof(info), _stream()))
+    keys = ("n_active", "n_clusters", "n_components", "n_core", "n_dead", "n_strips", "key_bits", "n_labelled")
+    return labels, dict(zip(keys, (int(v) for v in info)))
+
+
+def neighbour_counts_device(dx, dy, eps: int, cap: int = 0, cut: int = 0) -> torch.Tensor:
+    n = dx.numel()
+    out = torch.empty(n, dtype=torch.int32, device=dx.device)
+    check(_lib.lib().cloops_neighbour_counts(dx.data_ptr(), dy.data_ptr(), n, int(eps), int(cap), int(cut), out.data_ptr(), _stream()))
+    return out
+
+
+def cluster_summary_device(dx, dy, labels, n_clusters: int):
+    """bbox int32[K,4], size int32[K], kind uint8[K], row_kind uint8[n] (all CUDA tensors)."""
+    n = dx.numel()
+    k = int(n_clusters)
+    dev = dx.device
+    bbox = torch.empty((max(k, 1), 4), dtype=torch.int32, device=dev)
+    size = torch.empty(max(k, 1), dtype=torch.int32, device=dev)
+    kind = torch.empty(max(k, 1), dtype=torch.uint8, device=dev)
+    row_kind = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+    check(_lib.lib().cloops_cluster_summary(dx.data_ptr(), dy.data_ptr(), labels.data_ptr(), n, k, bbox.data_ptr(),
+                                            size.data_ptr(), kind.data_ptr(), row_kind.data_ptr(), _stream()))
+    return bbox[:k], size[:k], kind[:k], row_kind[:n]
+
+
+class Index:
+    """Resident (strip,u)-sorted index of one chromosome for one eps (cloops_index_* in the C ABI)."""
+
+    def __init__(self, dx: torch.Tensor, dy: torch.Tensor, eps: int, cut: int = 0):
+        self.n = dx.numel()
+        self._dx, self._dy = dx, dy           # keep inputs alive
+        h = C.c_void_p()
+        check(_lib.lib().cloops_index_build(dx.data_ptr(), dy.data_ptr(), self.n, int(eps), int(cut), C.byref(h), _stream()))
+        self._h = h
+        self.n_active = int(_lib.lib().cloops_index_n_active(h))
+
+    def count(self, cap: int, out: torch.Tensor | None = None) -> torch.Tensor:
+        if out is None:
+            out = torch.empty(max(self.n_active, 1), dtype=torch.int32, device=self._dx.device)
+        check(_lib.lib().cloops_index_count(self._h, int(cap), out.data_ptr(), _stream()))
+        return out
+
+    def dbscan(self, minPts: int, variant: int):
+        labels = torch.empty(self.n, dtype=torch.int32, device=self._dx.device)
+        info = (C.c_int64 * 8)()
+        check(_lib.lib().cloops_index_dbscan(self._h, int(minPts), int(variant), labels.data_ptr(), C.addressof(info), _stream()))
+        return labels, [int(v) for v in info]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            torch.cuda.current_stream().synchronize()
+            _lib.lib().cloops_index_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Coverage:
+    """Resident coverage model of one chromosome (cloops_coverage_* in the C ABI): PETs sorted by X
+    and by Y in HBM, the GPU form of the reference's getGenomeCoverage (cLoops/cModel.py:45-57)."""
+
+    def __init__(self, dx: torch.Tensor, dy: torch.Tensor):
+        self.n = dx.numel()
+        self.device = dx.device
+        h = C.c_void_p()
+        check(_lib.lib().cloops_coverage_build(dx.data_ptr(), dy.data_ptr(), self.n, C.byref(h), _stream()))
+        self._h = h
+
+    def _cand(self, cand) -> torch.Tensor:
+        cand = np.ascontiguousarray(np.asarray(cand, dtype=np.int64).reshape(-1, 4))
+        if cand.size and (cand.min() < -(1 << 31) or cand.max() >= (1 << 31)):
+            raise CloopsError("candidate interval outside int32")
+        return torch.from_numpy(cand.astype(np.int32)).to(self.device)
+
+    def range_counts(self, cand) -> np.ndarray:
+        """cand [m,4] = iva0, iva1, ivb0, ivb1  ->  int32 [m,123] (ra, rb, rab, na[10], nb[10], C[10x10])."""
+        d = self._cand(cand)
+        m = d.shape[0]
+        out = torch.empty((max(m, 1), 123), dtype=torch.int32, device=self.device)
+        check(_lib.lib().cloops_range_counts(self._h, d.data_ptr(), m, out.data_ptr(), _stream()))
+        return out[:m].cpu().numpy()
+
+    def region_pets(self, cand) -> np.ndarray:
+        """cand [m,4] -> int32 [m,3] = ra, rb, rab (getPETsforRegions, cModel.py:72-80)."""
+        d = self._cand(cand)
+        m = d.shape[0]
+        out = torch.empty((max(m, 1), 3), dtype=torch.int32, device=self.device)
+        check(_lib.lib().cloops_region_pets(self._h, d.data_ptr(), m, out.data_ptr(), _stream()))
+        return out[:m].cpu().numpy()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            torch.cuda.current_stream().synchronize()
+            _lib.lib().cloops_coverage_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,61 @@
+"""One pass of the whole hot path for one chromosome: cluster -> candidate records -> permuted-
+background range counts of every inter-ligation candidate.  This is the unit ``bench.py`` times and
+the composition ``pipe.singleDBSCAN`` + ``cModel.getIntSig`` perform per chromosome."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, device
+from ._lib import check
+
+
+class HotPathResult:
+    __slots__ = ("labels", "info", "bbox", "size", "kind", "row_kind", "cand", "counts")
+
+
+def run_device(dx: torch.Tensor, dy: torch.Tensor, eps: int, minPts: int, variant: int = _lib.V2, cut: int = 0,
+               score: bool = True) -> HotPathResult:
+    """Inputs and outputs resident in HBM.  ``counts`` is int32 [n_inter, 123] for the inter-ligation
+    candidates in ascending cluster-id order (cLoops/pipe.py:97, cModel.py:281-295)."""
+    r = HotPathResult()
+    r.labels, r.info = device.dbscan_device(dx, dy, eps, minPts, variant, cut)
+    r.bbox, r.size, r.kind, r.row_kind = device.cluster_summary_device(dx, dy, r.labels, r.info["n_clusters"])
+    r.cand = r.counts = None
+    if score:
+        cand = r.bbox[r.kind == 1].clamp_(min=0)[:, [0, 1, 2, 3]].contiguous()     # max(0, .) of cModel.py:281-282
+        m = cand.shape[0]
+        cov = device.Coverage(dx, dy)
+        out = torch.empty((max(m, 1), 123), dtype=torch.int32, device=dx.device)
+        if m:
+            check(_lib.lib().cloops_range_counts(cov._h, cand.data_ptr(), m, out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        cov.close()
+        r.cand, r.counts = cand, out[:m]
+    return r
+
+
+class HostStep:
+    """The same pass from HOST buffers: pinned int32 X, Y in; candidate records, per-PET kind bytes and
+    range counts out.  Staging buffers are allocated once and re-used."""
+
+    def __init__(self, n: int, device_index: int | None = None):
+        dev = torch.device("cuda", torch.cuda.current_device() if device_index is None else device_index)
+        self.dx = torch.empty(n, dtype=torch.int32, device=dev)
+        self.dy = torch.empty(n, dtype=torch.int32, device=dev)
+        self.h_row_kind = torch.empty(n, dtype=torch.uint8).pin_memory()
+        self.h2d_bytes = 2 * 4 * n
+        self.d2h_bytes = 0
+
+    def __call__(self, hx: torch.Tensor, hy: torch.Tensor, eps: int, minPts: int, variant: int = _lib.V2):
+        self.dx.copy_(hx, non_blocking=True)
+        self.dy.copy_(hy, non_blocking=True)
+        r = run_device(self.dx, self.dy, eps, minPts, variant)
+        self.h_row_kind.copy_(r.row_kind, non_blocking=True)
+        bbox = r.bbox.cpu()
+        kind = r.kind.cpu()
+        counts = r.counts.cpu()
+        torch.cuda.current_stream().synchronize()
+        self.d2h_bytes = self.h_row_kind.numel() + bbox.numel() * 4 + kind.numel() + counts.numel() * 4
+        return bbox, kind, counts, self.h_row_kind

@@ -1,0 +1,118 @@
+/*
+ * cloops_b200 -- C ABI of the B200-native cLoops hot path (libcloops_b200.so).
+ *
+ * Plain pointers and sizes only.  Pointers named d_* are DEVICE pointers on the current CUDA device,
+ * h_* are HOST pointers.  `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ * Every function returns 0 on success or a negative CLOOPS_E* code; cloops_last_error() returns the
+ * message of the last failure on the calling thread.  There is no CPU fallback anywhere.
+ *
+ * Reference interfaces replaced (paths relative to the cLoops 0.93 tree):
+ *   cloops_dbscan*           cLoops/cDBSCAN2.py:13-35 (v2, default, pipe.py:42), cLoops/cDBSCAN.py:12-40 (v1),
+ *                            cLoops/blockDBSCAN.py:13-41 (block): `DBSCAN(mat, eps, minPts).labels`
+ *   cloops_neighbour_counts  the eps-neighbourhood query: cDBSCAN.py:186-205 regionQuery,
+ *                            cDBSCAN2.py:304-346 getSparseCellNeighbor + :364-378 binSearchAdjPt
+ *   cloops_cluster_summary   cLoops/pipe.py:76-109 (per-cluster bbox, zero-extent drop, inter/self split,
+ *                            dis/dss membership)
+ *   cloops_range_counts      cLoops/cModel.py:60-143 (getCounts / getPETsforRegions /
+ *                            getNearbyPairRegions / the counting half of getMultiplePsFdr)
+ */
+#ifndef CLOOPS_B200_H
+#define CLOOPS_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define CLOOPS_API __attribute__((visibility("default")))
+#else
+#define CLOOPS_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CLOOPS_OK 0
+#define CLOOPS_EINVAL (-1)   /* bad argument (eps < 1, minPts < 1, n < 0, unknown variant ...) */
+#define CLOOPS_ERANGE (-2)   /* coordinates do not fit the packed 63-bit (strip,u,v) key */
+#define CLOOPS_ECUDA (-3)    /* CUDA runtime error; message in cloops_last_error() */
+#define CLOOPS_ENOMEM (-4)
+
+/* clusterer variants: same three classes the reference ships */
+#define CLOOPS_V1 1          /* cLoops.cDBSCAN.cDBSCAN        */
+#define CLOOPS_V2 2          /* cLoops.cDBSCAN2.cDBSCAN       */
+#define CLOOPS_BLOCK 3       /* cLoops.blockDBSCAN.blockDBSCAN */
+
+CLOOPS_API const char* cloops_last_error(void);
+CLOOPS_API const char* cloops_version(void);
+/* number of kernels launched by this library in this process so far (bench.py's gpu_launches) */
+CLOOPS_API int64_t cloops_kernel_launches(void);
+
+/* ---- stage timing (CUDA events on the caller's stream) ----------------------------------------
+ * With profiling on, every library call records per-stage events; after the call
+ * cloops_stage_count()/cloops_stage_name(i)/cloops_stage_ms(i) describe the stages of the LAST
+ * call on this thread (the call synchronises the stream when profiling is on). */
+CLOOPS_API void cloops_set_profiling(int on);
+CLOOPS_API int cloops_stage_count(void);
+CLOOPS_API const char* cloops_stage_name(int i);
+CLOOPS_API float cloops_stage_ms(int i);
+
+/* ---- clustering -------------------------------------------------------------------------------
+ * d_x, d_y: int32[n] PET anchor coordinates in ROW order (row = position in the reference's `mat`).
+ * cut > 0 drops rows with y - x < cut before clustering (pipe.py:59-63); they get label -1.
+ * d_labels: int32[n], row order; cluster ids EXACTLY as the reference numbers them, -1 = the point
+ * is absent from the reference's `labels` dict.
+ * h_info (may be NULL): int64[8] = {n_active, n_clusters (max id + 1), n_components, n_core,
+ *                                   n_dead (v2 released clusters), n_strips, key_bits, n_labelled}. */
+CLOOPS_API int cloops_dbscan(const int32_t* d_x, const int32_t* d_y, int64_t n, int32_t eps, int32_t minPts,
+                  int32_t cut, int32_t variant, int32_t* d_labels, int64_t* h_info, void* stream);
+
+/* Host-buffer form of the reference boundary `DBSCAN(mat, eps, minPts).labels`:
+ * h_mat int64[n,3] rows [pointId, X, Y] (pipe.py:70); h_labels int64[n] row order, -1 = absent.
+ * Copies in, clusters on the GPU, copies out. */
+CLOOPS_API int cloops_dbscan_host(const int64_t* h_mat, int64_t n, int32_t eps, int32_t minPts, int32_t variant,
+                       int64_t* h_labels, int64_t* h_info);
+
+/* Region query alone: d_counts[row] = min(cap, #{q : |dX|+|dY| <= eps}) counting the point itself
+ * (cDBSCAN.py:196-204).  cap <= 0 means no saturation. Rows removed by `cut` get 0. */
+CLOOPS_API int cloops_neighbour_counts(const int32_t* d_x, const int32_t* d_y, int64_t n, int32_t eps, int32_t cap,
+                            int32_t cut, int32_t* d_counts, void* stream);
+
+/* ---- resident index, for sweeps and for timing the region-query kernel in isolation -------------
+ * The index is the HBM layout of one chromosome for one eps: points sorted by (v-strip, u) as packed
+ * 64-bit keys, the row permutation and the dense strip-offset table. */
+typedef struct cloops_index cloops_index;
+CLOOPS_API int cloops_index_build(const int32_t* d_x, const int32_t* d_y, int64_t n, int32_t eps, int32_t cut,
+                       cloops_index** out, void* stream);
+CLOOPS_API void cloops_index_free(cloops_index* ix);
+CLOOPS_API int64_t cloops_index_n_active(const cloops_index* ix);
+/* one launch of the region-query kernel over the index; d_counts_sorted int32[n_active] in index order */
+CLOOPS_API int cloops_index_count(cloops_index* ix, int32_t cap, int32_t* d_counts_sorted, void* stream);
+/* labels for one minPts over a built index (v1/v2 only) */
+CLOOPS_API int cloops_index_dbscan(cloops_index* ix, int32_t minPts, int32_t variant, int32_t* d_labels,
+                        int64_t* h_info, void* stream);
+
+/* ---- cluster -> candidate records (pipe.py:76-109) ---------------------------------------------
+ * n_clusters = max id + 1.  d_bbox int32[n_clusters,4] = minX,maxX,minY,maxY ; d_size int32[n_clusters]
+ * (0 for unused ids); d_kind uint8[n_clusters]: 0 unused/dropped (zero extent, pipe.py:83-85),
+ * 1 inter-ligation (maxX < minY, pipe.py:97), 2 self-ligation; d_row_kind uint8[n] (may be NULL):
+ * kind of the row's cluster, 0 for unlabelled rows (membership of dis / dss, pipe.py:106-109). */
+CLOOPS_API int cloops_cluster_summary(const int32_t* d_x, const int32_t* d_y, const int32_t* d_labels, int64_t n,
+                           int64_t n_clusters, int32_t* d_bbox, int32_t* d_size, uint8_t* d_kind,
+                           uint8_t* d_row_kind, void* stream);
+
+/* ---- permuted-local-background range counts (cModel.py:60-143) ---------------------------------
+ * A coverage model is the chromosome's PETs sorted once by X and once by Y (the reference's
+ * getGenomeCoverage, cModel.py:45-57). */
+typedef struct cloops_coverage cloops_coverage;
+CLOOPS_API int cloops_coverage_build(const int32_t* d_x, const int32_t* d_y, int64_t n, cloops_coverage** out, void* stream);
+CLOOPS_API void cloops_coverage_free(cloops_coverage* cov);
+/* d_cand int32[m,4] = iva0, iva1, ivb0, ivb1 (already clamped at 0, cModel.py:281-282);
+ * d_out int32[m,123] = ra, rb, rab, na[10], nb[10], C[10][10] row-major (i over A windows). */
+CLOOPS_API int cloops_range_counts(const cloops_coverage* cov, const int32_t* d_cand, int64_t m, int32_t* d_out, void* stream);
+/* only ra, rb, rab (getPETsforRegions, cModel.py:72-80): d_out int32[m,3] */
+CLOOPS_API int cloops_region_pets(const cloops_coverage* cov, const int32_t* d_cand, int64_t m, int32_t* d_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -398,3 +398,53 @@ def stats_from_counts(c: np.ndarray, N: int):
     bp = np.mean(nbps) * ra * rb / N
     nbp = max([1e-300, binom.sf(rab - 1.0, N - rab, bp)])
     return ra, rb, rab, es, fdr, hyp, pop, nbp
+
+
+# --------------------------------------------------------------------------------------------------
+# The same counts the way the reference obtains them (cModel.py:31-80,108-143): sorted coordinate
+# arrays + searchsorted slices + set algebra on row indices.  Used for the CPU baseline timing; the
+# brute-force range_counts() above stays the independent check.
+
+
+class CoverageIndex:
+    def __init__(self, X, Y):
+        X = np.asarray(X, np.int64)
+        Y = np.asarray(Y, np.int64)
+        self.N = len(X)
+        self.ox = np.argsort(X, kind="stable")          # cModel.py:41 np.sort(cs) + row lists (:38-40)
+        self.kx = X[self.ox]
+        self.oy = np.argsort(Y, kind="stable")
+        self.ky = Y[self.oy]
+
+    def _rows(self, keys, order, iv):                   # getCounts, cModel.py:60-69
+        a = np.searchsorted(keys, iv[0], side="left")
+        b = np.searchsorted(keys, iv[1], side="right")
+        return order[a:b]
+
+    def either(self, iv):                               # source-union-target, cModel.py:73-78,118-127
+        return np.union1d(self._rows(self.kx, self.ox, iv), self._rows(self.ky, self.oy, iv))
+
+    def range_counts(self, iva, ivb, win=5) -> np.ndarray:
+        ra = len(self.either(iva))
+        rb = len(self.either(ivb))
+        rab = len(np.intersect1d(self._rows(self.kx, self.ox, iva), self._rows(self.ky, self.oy, ivb), assume_unique=True))
+        ivas, ivbs = nearby_windows(iva, ivb, win)
+        sa = [self.either(w) for w in ivas]
+        sb = [self.either(w) for w in ivbs]
+        out = [ra, rb, rab] + [len(s) for s in sa] + [len(s) for s in sb]
+        for a in sa:
+            for b in sb:
+                out.append(len(np.intersect1d(a, b, assume_unique=True)))
+        return np.array(out, dtype=np.int64)
+
+
+def hot_path_cpu(X, Y, eps, minPts):
+    """One pass of the whole hot path on the CPU (clusterer v2 -> candidate records -> range counts of
+    every inter-ligation candidate); returns (labels, inter records, counts[K,123])."""
+    lab = cdbscan_v2(X, Y, eps, minPts)
+    inter, selfl, in_i, in_s = cluster_records(X, Y, lab)
+    cov = CoverageIndex(X, Y)
+    counts = np.zeros((len(inter), 123), np.int64)
+    for k, r in enumerate(inter):
+        counts[k] = cov.range_counts([max(0, int(r[0])), int(r[1])], [max(0, int(r[2])), int(r[3])])
+    return lab, inter, counts
