@@ -1,0 +1,160 @@
+"""CPU tests of the host side: statistics tail, loop de-duplication, file formats, cut estimation,
+chromosome sharding (world_size 2 over gloo).  No GPU, no reference tree needed (golden vectors)."""
+import gzip
+import logging
+import os
+import subprocess
+import sys
+
+import joblib
+import numpy as np
+import pandas as pd
+import pytest
+
+from cloops_b200 import cModel, dist, ests, io, pipe
+from oracle import ref_shim
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def gold(gold_dir):
+    return np.load(os.path.join(gold_dir, "chr21_m1_pipe.npz"))
+
+
+def test_stats_tail_matches_reference_tuples(gold):
+    N = int(gold["sig_N"])
+    for k in range(200):
+        got = cModel._stats(gold["sig_ints200"][k].astype(np.int32), N)
+        want = gold["sig_tuples"][k][5:]
+        assert tuple(float(x) for x in got) == tuple(float(x) for x in want), k
+
+
+def test_scoring_tail_reproduces_loop_file(gold, gold_dir, tmp_path):
+    """From the reference's per-candidate tuples, the host tail (key numbering, removeDup x2,
+    Bonferroni, markIntSig, to_csv) must reproduce the reference's .loop byte for byte."""
+    tup = gold["sig_tuples"]
+    ds, i = {}, 0
+    for t in tup:
+        a0, a1, b0, b1 = (int(x) for x in t[:4])
+        ra, rb, rab = int(t[5]), int(t[6]), int(t[7])
+        if rab < 5:
+            continue
+        key = "chr21-chr21-%d" % i
+        i += 1
+        ds[key] = {"distance": abs((b0 + b1) / 2.0 - (a0 + a1) / 2.0), "ra": ra, "rb": rb, "rab": rab, "ES": t[8], "FDR": t[9],
+                   "hypergeometric_p-value": t[10], "poisson_p-value": t[11], "binomial_p-value": t[12],
+                   "iva": "chr21:%d-%d" % (a0, a1), "ivb": "chr21:%d-%d" % (b0, b1)}
+    ds = cModel.removeDup(cModel.removeDup(ds))
+    tab = pd.DataFrame(ds).T
+    tab["poisson_p-value_corrected"] = cModel.getBonPvalues(tab["poisson_p-value"])
+    tab["binomial_p-value_corrected"] = cModel.getBonPvalues(tab["binomial_p-value"])
+    tab["hypergeometric_p-value_corrected"] = cModel.getBonPvalues(tab["hypergeometric_p-value"])
+    tab = cModel.markIntSig(tab)
+    out = tmp_path / "t.loop"
+    tab.to_csv(out, sep="\t", index_label="loopId")
+    assert open(out, "rb").read() == open(os.path.join(gold_dir, "chr21_m1.loop"), "rb").read()
+    assert int(tab["significant"].sum()) == 202 and len(tab) == 343
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not mounted")
+def test_removedup_and_marks_vs_live_reference():
+    ns = ref_shim.load()
+    rng = np.random.default_rng(11)
+    for trial in range(20):
+        n = int(rng.integers(1, 120))
+        ds = {}
+        for k in range(n):
+            a0 = int(rng.integers(0, 3000)); a1 = a0 + int(rng.integers(0, 300))
+            b0 = a0 + int(rng.integers(200, 3000)); b1 = b0 + int(rng.integers(0, 300))
+            c = "chr%d" % rng.integers(1, 3)
+            ds["%s-%s-%d" % (c, c, k)] = {"iva": "%s:%d-%d" % (c, a0, a1), "ivb": "%s:%d-%d" % (c, b0, b1),
+                                          "rab": int(rng.integers(1, 30)), "ra": int(rng.integers(30, 90)), "rb": int(rng.integers(30, 90)),
+                                          "binomial_p-value": float(10 ** -rng.uniform(2, 9)), "ES": float(rng.uniform(0, 5)),
+                                          "FDR": float(rng.choice([0.0, 0.01, 0.02])), "poisson_p-value": float(10 ** -rng.uniform(2, 9)),
+                                          "hypergeometric_p-value": float(10 ** -rng.uniform(5, 15))}
+        got, want = cModel.removeDup(dict(ds)), ns.cModel.removeDup(dict(ds))
+        assert list(got.keys()) == list(want.keys()), trial
+        if len(want):
+            a, b = pd.DataFrame(got).T, pd.DataFrame(want).T
+            assert cModel.markIntSig(a.copy())["significant"].tolist() == ns.cModel.markIntSig(b.copy())["significant"].tolist()
+            assert cModel.markIntSigHic(a.copy())["significant"].tolist() == ns.cModel.markIntSigHic(b.copy())["significant"].tolist()
+
+
+def test_nearby_windows_and_overlap():
+    ivas, ivbs = cModel.getNearbyPairRegions([100, 301], [1000, 1400])
+    assert len(ivas) == len(ivbs) == 10
+    assert ivas[0] == [0, 0] and ivas[4] == [0, 150] and ivas[5] == [250, 450]        # clamped at 0 (cModel.py:98-102)
+    assert cModel.checkOverlap(["c", 1, 5], ["c", 10, 20], ["c", 5, 9], ["c", 20, 30]) is True
+    assert cModel.checkOverlap(["c", 1, 5], ["c", 10, 20], ["d", 5, 9], ["c", 20, 30]) is None
+    assert cModel.checkOverlap(["c", 1, 5], ["c", 10, 20], ["c", 6, 9], ["c", 20, 30]) is False
+
+
+def test_bedpe_ingest_and_jd(tmp_path):
+    lines = ["chr1\t100\t200\tchr1\t1000\t1101\tp0\t.\t+\t-",       # cA=150, cB=1050
+             "chr1\t5000\t5003\tchr1\t10\t20\tp1\t.\t+\t+",         # swapped: cA=15, cB=5001
+             "chr1\t1\t2\tchr2\t3\t4\tp2\t.\t+\t-",                 # trans: dropped
+             "chr2\t7\t8\tchr2\t9\t12\tp3\t.\t-\t-",
+             "*\t-1\t-1\t*\t-1\t-1\tp4\t.\t+\t-", "short\tline",
+             "chr1\t100\t200\tchr1\t1000\t1101\tdup\t.\t+\t-"]
+    f = tmp_path / "a.bedpe.gz"
+    with gzip.open(f, "wt") as fh:
+        fh.write("\n".join(lines) + "\n")
+    log = logging.getLogger("t")
+    out = tmp_path / "o"
+    os.mkdir(out)
+    cfs = io.parseRawBedpe2([str(f)], str(out), [], 0, log)
+    assert [os.path.basename(c) for c in cfs] == ["chr1-chr1.jd", "chr2-chr2.jd"]
+    key, mat = io.parseJd(cfs[0])
+    assert key == ("chr1", "chr1") and mat.dtype == np.int64
+    assert mat.tolist() == [[0, 150, 1050], [1, 15, 5001], [2, 150, 1050]]
+    assert io.parseJd(cfs[0], cut=1000)[1].tolist() == [[1, 15, 5001]]
+    out2 = tmp_path / "o2"
+    os.mkdir(out2)
+    cfs2, dsts = io.parseRawBedpe([str(f)], str(out2), {"chr1"}, 0, log)
+    assert io.parseJd(cfs2[0])[1].tolist() == [[0, 150, 1050], [1, 15, 5001]] and dsts == [900]
+    txt = tmp_path / "chr9-chr9.txt"
+    txt.write_text("0\t5\t9\n1\t6\t10\n")
+    assert joblib.load(io.txt2jd(str(txt))).tolist() == [[0, 5, 9], [1, 6, 10]] and not txt.exists()
+    assert io.parseIv("chr21:44800894-44801696") == ["chr21", 44800894, 44801696]
+
+
+def test_cut_estimation_and_round_helpers(gold):
+    rng = np.random.default_rng(0)
+    di = rng.integers(5000, 500000, 4000).astype(float)
+    dsv = rng.integers(50, 3000, 6000).astype(float)
+    cut, frag = ests.estIntSelCutFrag(di, dsv)
+    lds, ldi = np.log2(dsv), np.log2(di)
+    want = int(2 ** min(np.median(lds) + 3 * lds.std(), (lds.mean() * lds.std() + ldi.mean() * ldi.std()) / (lds.std() + ldi.std())))
+    assert cut == want and frag == int(2 ** np.median(lds))
+    assert ests.estFragSize([100] * 5 + [200] * 3 + [300]) == 200
+    if ref_shim.available():
+        ns = ref_shim.load()
+        assert ns.ests.estIntSelCutFrag(di, dsv) == (cut, frag)
+    a = {("c", "c"): {"f": "f", "records": [["c", 1, 2, "c", 30, 40], ["c", 5, 6, "c", 7, 9]]}}
+    b = {("c", "c"): {"f": "f", "records": [["c", 1, 2, "c", 30, 40], ["c", 1, 3, "c", 30, 40]]},
+         ("d", "d"): {"f": "g", "records": [["d", 1, 2, "d", 3, 4]]}}
+    m = pipe.combineTwice(a, b)
+    assert [r[1:3] + r[4:6] for r in m[("c", "c")]["records"]] == [[1, 2, 30, 40], [5, 6, 7, 9], [1, 3, 30, 40]]
+    assert ("d", "d") in m
+    f = pipe.filterClusterByDis(m, 20)
+    assert [r[1:3] for r in f[("c", "c")]["records"]] == [[1, 2], [1, 3]]
+    assert pipe._int_list("2000,500,1000", False) == [500, 1000, 2000] and pipe._int_list("20,50", True) == [50, 20]
+    assert pipe._int_list(0, False) == 0 and pipe._int_list("7", True) == [7]
+
+
+def test_lpt_assignment():
+    owner = dist.assign(list("abcdefgh"), [13, 12, 10, 9, 8, 7, 5, 1], nranks=4)
+    loads = [sum(w for w, o in zip([13, 12, 10, 9, 8, 7, 5, 1], owner) if o == r) for r in range(4)]
+    assert max(loads) - min(loads) <= 3 and sorted(set(owner)) == [0, 1, 2, 3]
+    assert dist.my_share(["x", "y"]) == ["x", "y"] and dist.merge_in_order(["x"], {"x": 1}) == [1]
+
+
+def test_two_rank_gloo(tmp_path):
+    """N>1 path on CPU: two processes over gloo shard five chromosomes and merge per-round results."""
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", CUDA_VISIBLE_DEVICES="")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29631", os.path.join(ROOT, "tests", "_dist_worker.py"), str(tmp_path)]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert (tmp_path / "ok").exists()
