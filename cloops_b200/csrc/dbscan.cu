@@ -36,8 +36,20 @@ struct Work {
     int* ids;        // [n+1]
     int* list_und;   // [n_act] undecided roots
     int* list_con;   // [n_act] contested border points
-    int* counters;   // [8]: 0 n_und, 1 n_con, 2 remaining, 3 n_dead, 4 n_comp, 5 n_core, 6 n_labelled
+    int* counters;   // [8]: 0 n_und, 1 n_con, 2 remaining, 3 n_dead, 4 n_comp
+    int* slots_core; // [CTR_SLOTS*CTR_STRIDE] spread partial sums of n_core
+    int* slots_lab;  // same for n_labelled
 };
+
+// Informational totals (n_core, n_labelled): one atomic per CTA, spread over CTR_SLOTS addresses 128 B
+// apart -- the L2 atomic unit serialises same-address atomics (~0.5 us per thousand), which made a
+// per-warp counter the slowest part of otherwise streaming kernels.
+#define CTR_SLOTS 32
+#define CTR_STRIDE 32
+__device__ __forceinline__ void block_count(int* slots, bool pred) {
+    const int total = __syncthreads_count(pred);
+    if (threadIdx.x == 0 && total) atomicAdd(&slots[(blockIdx.x % CTR_SLOTS) * CTR_STRIDE], total);
+}
 
 __global__ void __launch_bounds__(256) fill_int_kernel(int* p, int v, long long n) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -47,28 +59,30 @@ __global__ void __launch_bounds__(256) fill_int_kernel(int* p, int v, long long 
 // core flag into bit 63 of the key; union-find and per-root state initialised
 __global__ void __launch_bounds__(256) flag_kernel(u64* __restrict__ keys, GridParams P, int minPts, Work W, int want_cells) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.n_act) return;
-    u64 k = keys[i] & KEY_MASK;
-    bool core = W.cnt[i] >= minPts;
-    keys[i] = core ? (k | CORE_FLAG) : k;
-    W.parent[i] = i;
-    W.rank[i] = INT_MAX;
-    W.ncore[i] = 0;
-    W.size[i] = 0;
-    W.status[i] = ST_NONE;
-    if (want_cells) {
-        // rotated floor cell = (strip, floor(u'/eps)) (cDBSCAN2.py:69-70); head = first sorted point of the cell
-        bool head = true;
-        if (i > 0) {
-            u64 kp = keys[i - 1] & KEY_MASK;   // flag bit of a neighbour may or may not be set yet: masked
-            u32 cu = ((u32)(k >> P.be) & P.umask) / (u32)P.eps;
-            u32 cup = ((u32)(kp >> P.be) & P.umask) / (u32)P.eps;
-            head = (k >> P.sshift) != (kp >> P.sshift) || cu != cup;
+    bool core = false;
+    if (i < P.n_act) {
+        u64 k = keys[i] & KEY_MASK;
+        core = W.cnt[i] >= minPts;
+        keys[i] = core ? (k | CORE_FLAG) : k;
+        W.parent[i] = i;
+        W.rank[i] = INT_MAX;
+        W.ncore[i] = 0;
+        W.size[i] = 0;
+        W.status[i] = ST_NONE;
+        if (want_cells) {
+            // rotated floor cell = (strip, floor(u'/eps)) (cDBSCAN2.py:69-70); head = first sorted point of the cell
+            bool head = true;
+            if (i > 0) {
+                u64 kp = keys[i - 1] & KEY_MASK;   // flag bit of a neighbour may or may not be set yet: masked
+                u32 cu = ((u32)(k >> P.be) & P.umask) / (u32)P.eps;
+                u32 cup = ((u32)(kp >> P.be) & P.umask) / (u32)P.eps;
+                head = (k >> P.sshift) != (kp >> P.sshift) || cu != cup;
+            }
+            W.chead[i] = head ? i : 0;
+            W.cellmin[i] = INT_MAX;
         }
-        W.chead[i] = head ? i : 0;
-        W.cellmin[i] = INT_MAX;
     }
-    if (core) atomicAdd(&W.counters[5], 1);
+    block_count(W.slots_core, core);
 }
 
 __global__ void __launch_bounds__(256) cellmin_kernel(const u32* __restrict__ rows, GridParams P, Work W) {
@@ -136,18 +150,26 @@ __global__ void __launch_bounds__(256) union_kernel(const u64* __restrict__ keys
     }
 }
 
-// full compression + per-component statistics
+// full compression + per-component statistics.  Sorted order is spatially coherent, so lanes of a warp
+// mostly share a root: statistics are reduced per (warp, root) group before touching global atomics
+// (the giant diagonal component would otherwise serialise millions of same-address atomics).
 __global__ void __launch_bounds__(256) compress_kernel(const u64* __restrict__ keys, const u32* __restrict__ rows, GridParams P,
                                                        Work W, int variant) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.n_act) return;
-    if (!(keys[i] >> 63)) { W.assigned[i] = -1; return; }
+    const bool core = (i < P.n_act) && (keys[i] >> 63);
+    if (i < P.n_act && !core) W.assigned[i] = -1;
+    const unsigned cm = __ballot_sync(0xffffffffu, core);
+    if (!core) return;
     int r = uf_find(W.parent, i);
     W.parent[i] = r;
     W.assigned[i] = r;
-    atomicAdd(&W.ncore[r], 1);
     int rk = (variant == CLOOPS_V1) ? (int)rows[i] : W.cellmin[W.chead[i]];
-    atomicMin(&W.rank[r], rk);
+    const unsigned m = __match_any_sync(cm, r);
+    const int vmin = __reduce_min_sync(m, rk);
+    if ((int)(threadIdx.x & 31) == __ffs(m) - 1) {
+        atomicAdd(&W.ncore[r], __popc(m));
+        atomicMin(&W.rank[r], vmin);
+    }
     if (r == i) atomicAdd(&W.counters[4], 1);
 }
 
@@ -198,23 +220,6 @@ __global__ void __launch_bounds__(256) v2_status_kernel(const u64* __restrict__ 
         W.status[i] = ST_UNDECIDED;
         W.list_und[atomicAdd(&W.counters[0], 1)] = i;
     }
-}
-
-// border points adjacent to at least one undecided component
-__global__ void __launch_bounds__(256) v2_contested_kernel(const u64* __restrict__ keys, const int* __restrict__ sstart,
-                                                           GridParams P, Work W) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.n_act) return;
-    const u64 key = keys[i];
-    if (key >> 63) return;
-    const PointView p = view(key, P);
-    bool hit = false;
-    for_each_neighbour(keys, sstart, P, i, p, [&](int j, u64 kq) {
-        if (!(kq >> 63)) return true;
-        if (W.status[root_of(W.parent, j)] == ST_UNDECIDED) { hit = true; return false; }
-        return true;
-    });
-    if (hit) W.list_con[atomicAdd(&W.counters[1], 1)] = i;
 }
 
 __global__ void __launch_bounds__(256) v2_reset_kernel(Work W, int n_und) {
@@ -272,24 +277,32 @@ __global__ void __launch_bounds__(256) v2_decide_kernel(Work W, int n_und, int m
     else atomicAdd(&W.counters[2], 1);
 }
 
-// final v2 ownership: lowest-ranked alive adjacent component (cDBSCAN2.py:130,162,352)
+// v2 ownership: lowest-ranked non-dead adjacent component (cDBSCAN2.py:130,162,352).  The first pass
+// (FIX = false, every non-core point, nothing dead yet) also queues the points adjacent to an undecided
+// component; after the survival rounds only those are re-evaluated (FIX = true).
+template <bool FIX>
 __global__ void __launch_bounds__(256) v2_border_kernel(const u64* __restrict__ keys, const int* __restrict__ sstart,
-                                                        GridParams P, Work W) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.n_act) return;
+                                                        GridParams P, Work W, int n_items) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_items) return;
+    const int i = FIX ? W.list_con[t] : t;
     const u64 key = keys[i];
-    if (key >> 63) return;
+    if (!FIX && (key >> 63)) return;
     const PointView p = view(key, P);
     int best_rank = INT_MAX, best_root = -1;
+    bool contested = false;
     for_each_neighbour(keys, sstart, P, i, p, [&](int j, u64 kq) {
         if (!(kq >> 63)) return true;
         int r = root_of(W.parent, j);
-        if (W.status[r] == ST_DEAD) return true;
+        unsigned char st = W.status[r];
+        if (st == ST_DEAD) return true;
+        if (st == ST_UNDECIDED) contested = true;
         int rk = W.rank[r];
         if (rk < best_rank) { best_rank = rk; best_root = r; }
         return true;
     });
     W.assigned[i] = best_root;
+    if (!FIX && contested) W.list_con[atomicAdd(&W.counters[1], 1)] = i;
 }
 
 // ---- numbering ----------------------------------------------------------------------------------------
@@ -305,15 +318,16 @@ __global__ void __launch_bounds__(256) number_flags_kernel(const u64* __restrict
 __global__ void __launch_bounds__(256) label_kernel(const u32* __restrict__ rows, GridParams P, Work W, int variant, int minPts,
                                                     int* __restrict__ labels) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.n_act) return;
-    int a = W.assigned[i];
     int lab = -1;
-    if (a >= 0) {
-        bool keep = (variant == CLOOPS_V1) ? (W.size[a] >= minPts) : (W.status[a] != ST_DEAD);
-        if (keep) lab = W.ids[W.rank[a]];
+    if (i < P.n_act) {
+        int a = W.assigned[i];
+        if (a >= 0) {
+            bool keep = (variant == CLOOPS_V1) ? (W.size[a] >= minPts) : (W.status[a] != ST_DEAD);
+            if (keep) lab = W.ids[W.rank[a]];
+        }
+        labels[rows[i]] = lab;
     }
-    labels[rows[i]] = lab;
-    if (lab >= 0) atomicAdd(&W.counters[6], 1);
+    block_count(W.slots_lab, lab >= 0);
 }
 
 int index_dbscan(cloops_index* ix, int minPts, int variant, int* d_labels, int64_t* h_info, cudaStream_t st) {
@@ -322,7 +336,7 @@ int index_dbscan(cloops_index* ix, int minPts, int variant, int* d_labels, int64
     if (variant != CLOOPS_V1 && variant != CLOOPS_V2) return fail(CLOOPS_EINVAL, "variant %d not served by the strip index", variant);
     if (h_info) for (int k = 0; k < 8; ++k) h_info[k] = 0;
     if (P.n == 0) return 0;
-    LAUNCH(fill_int_kernel, cdiv(P.n, 256), 256, 0, st, d_labels, -1, (long long)P.n);
+    if (P.n_act < P.n) LAUNCH(fill_int_kernel, cdiv(P.n, 256), 256, 0, st, d_labels, -1, (long long)P.n);
     if (P.n_act == 0) return 0;
     const int na = P.n_act, g = cdiv(na, 256);
     Temp tmp(st);
@@ -337,7 +351,7 @@ int index_dbscan(cloops_index* ix, int minPts, int variant, int* d_labels, int64
     RET_IF(tmp.alloc(&W.status, na));
     RET_IF(tmp.alloc(&W.flags, (size_t)P.n + 1));
     RET_IF(tmp.alloc(&W.ids, (size_t)P.n + 1));
-    RET_IF(tmp.alloc(&W.counters, 8));
+    RET_IF(tmp.alloc(&W.counters, 8 + 2 * CTR_SLOTS * CTR_STRIDE));
     W.chead = W.cellmin = W.list_und = W.list_con = nullptr;
     const bool v2 = variant == CLOOPS_V2;
     if (v2) {
@@ -346,7 +360,9 @@ int index_dbscan(cloops_index* ix, int minPts, int variant, int* d_labels, int64
         RET_IF(tmp.alloc(&W.list_und, na));
         RET_IF(tmp.alloc(&W.list_con, na));
     }
-    CU_TRY(cudaMemsetAsync(W.counters, 0, 8 * sizeof(int), st));
+    CU_TRY(cudaMemsetAsync(W.counters, 0, (8 + 2 * CTR_SLOTS * CTR_STRIDE) * sizeof(int), st));
+    W.slots_core = W.counters + 8;
+    W.slots_lab = W.counters + 8 + CTR_SLOTS * CTR_STRIDE;
     CU_TRY(cudaMemsetAsync(W.flags, 0, ((size_t)P.n + 1) * sizeof(int), st));
 
     RET_IF(index_count(ix, minPts, W.cnt, st));
@@ -373,14 +389,12 @@ int index_dbscan(cloops_index* ix, int minPts, int variant, int* d_labels, int64
         stage_mark("border", st);
     } else {
         LAUNCH(v2_status_kernel, g, 256, 0, st, ix->keys, P, minPts, W);
+        LAUNCH(v2_border_kernel<false>, g, 256, 0, st, ix->keys, ix->sstart, P, W, na);
+        stage_mark("border", st);
         CU_TRY(cudaMemcpyAsync(counters, W.counters, sizeof(counters), cudaMemcpyDeviceToHost, st));
         CU_TRY(cudaStreamSynchronize(st));
-        int n_und = counters[0];
+        const int n_und = counters[0], n_con = counters[1];
         if (n_und > 0) {
-            LAUNCH(v2_contested_kernel, g, 256, 0, st, ix->keys, ix->sstart, P, W);
-            CU_TRY(cudaMemcpyAsync(counters, W.counters, sizeof(counters), cudaMemcpyDeviceToHost, st));
-            CU_TRY(cudaStreamSynchronize(st));
-            int n_con = counters[1];
             for (int round = 0;; ++round) {
                 LAUNCH(v2_reset_kernel, cdiv(n_und, 256), 256, 0, st, W, n_und);
                 if (n_con > 0) LAUNCH(v2_accumulate_kernel, cdiv(n_con, 128), 128, 0, st, ix->keys, ix->sstart, P, W, n_con);
@@ -390,10 +404,10 @@ int index_dbscan(cloops_index* ix, int minPts, int variant, int* d_labels, int64
                 if (counters[2] == 0) break;
                 if (round > na) return fail(CLOOPS_ECUDA, "v2 survival did not converge");
             }
+            if (n_con > 0 && counters[3] > 0)
+                LAUNCH(v2_border_kernel<true>, cdiv(n_con, 256), 256, 0, st, ix->keys, ix->sstart, P, W, n_con);
         }
         stage_mark("survival", st);
-        LAUNCH(v2_border_kernel, g, 256, 0, st, ix->keys, ix->sstart, P, W);
-        stage_mark("border", st);
     }
     LAUNCH(number_flags_kernel, g, 256, 0, st, ix->keys, P, W, variant);
     {
@@ -407,17 +421,24 @@ int index_dbscan(cloops_index* ix, int minPts, int variant, int* d_labels, int64
     stage_mark("labels", st);
     if (h_info) {
         int n_clusters = 0;
+        static thread_local int slots[2 * CTR_SLOTS * CTR_STRIDE];
         CU_TRY(cudaMemcpyAsync(counters, W.counters, sizeof(counters), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaMemcpyAsync(slots, W.slots_core, sizeof(slots), cudaMemcpyDeviceToHost, st));
         CU_TRY(cudaMemcpyAsync(&n_clusters, W.ids + P.n, sizeof(int), cudaMemcpyDeviceToHost, st));
         CU_TRY(cudaStreamSynchronize(st));
+        long long n_core = 0, n_lab = 0;
+        for (int k = 0; k < CTR_SLOTS; ++k) {
+            n_core += slots[k * CTR_STRIDE];
+            n_lab += slots[(CTR_SLOTS + k) * CTR_STRIDE];
+        }
         h_info[0] = P.n_act;
         h_info[1] = n_clusters;
         h_info[2] = counters[4];
-        h_info[3] = counters[5];
+        h_info[3] = n_core;
         h_info[4] = counters[3];
         h_info[5] = P.ns;
         h_info[6] = P.be + P.bu + P.bs;
-        h_info[7] = counters[6];
+        h_info[7] = n_lab;
     }
     return 0;
 }

@@ -89,12 +89,20 @@ __global__ void __launch_bounds__(256) strip_table_search_kernel(const u64* __re
 
 // --------------------------------------------------------------------------------------------------
 // Region query: neighbour count per point, saturating at cap (cDBSCAN.py:186-205; cDBSCAN2.py:304-346).
-// One thread per sorted point; consecutive threads are spatial neighbours, so the three runs they walk
-// overlap and are served from L1/L2.
-__global__ void __launch_bounds__(256) count_kernel(const u64* __restrict__ keys, const int* __restrict__ sstart, GridParams P,
-                                                    int cap, int* __restrict__ cnt) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.n_act) return;
+//
+// A CTA owns TILE consecutive sorted points.  Everything its threads can touch -- the strips of the
+// tile plus one strip below and one above -- is ONE contiguous key range R (strips are consecutive in
+// the sort order), staged once into shared memory as 32-bit u' and vmod arrays with coalesced loads.
+// Phase 1 (every thread): walk left/right inside the own strip; dense points saturate here.
+// Phase 2 (compacted): the still unsaturated points are queued in shared memory so that full warps run
+// the two binary searches + window scans of strips s-1 and s+1.
+// If R does not fit (very long strips: dense Hi-C diagonals, where phase 1 saturates almost at once)
+// the CTA falls back to the same walk on global memory through L1.
+#define CQ_TILE 256
+#define CQ_RMAX 2048
+
+__device__ __forceinline__ int count_point_global(const u64* __restrict__ keys, const int* __restrict__ sstart, const GridParams& P,
+                                                  int cap, int i) {
     const PointView p = view(keys[i], P);
     const int lo_s = __ldg(sstart + p.s + 1), hi_s = __ldg(sstart + p.s + 2);
     int c = 1;
@@ -132,7 +140,136 @@ __global__ void __launch_bounds__(256) count_kernel(const u64* __restrict__ keys
             }
         }
     }
-    cnt[i] = c;
+    return c;
+}
+
+__device__ __forceinline__ int lower_bound_s(const u32* __restrict__ U, int lo, int hi, u32 target) {   // first U >= target
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (U[mid] < target) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+__device__ __forceinline__ int upper_bound_s(const u32* __restrict__ U, int lo, int hi, u32 target) {   // first U > target
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (U[mid] <= target) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// window of an adjacent strip [a,b): 4 predicated probes from the lower bound (no divergence), then a
+// tail loop for the rare longer windows.  UPPER: strip s-1 needs vmod_q >= vmod_p, strip s+1 vmod_q <= vmod_p.
+template <bool PREV>
+__device__ __forceinline__ int adjacent_strip_count(const u32* __restrict__ U, const u32* __restrict__ V, int a, int b, int me,
+                                                    u32 ulo, u32 uhi, u32 vm, int c, int cap) {
+    int j = lower_bound_s(U, a, b, ulo);
+    bool in = true;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int jj = j + k;
+        in = in && jj < b;
+        const int js = in ? jj : me;
+        in = in && U[js] <= uhi;
+        const u32 vq = V[js];
+        c += (in && (PREV ? vq >= vm : vq <= vm)) ? 1 : 0;
+    }
+    if (in) {
+        for (int jj = j + 4; jj < b && c < cap; ++jj) {
+            if (U[jj] > uhi) break;
+            const u32 vq = V[jj];
+            c += (PREV ? vq >= vm : vq <= vm) ? 1 : 0;
+        }
+    }
+    return c;
+}
+
+__global__ void __launch_bounds__(CQ_TILE) count_kernel(const u64* __restrict__ keys, const int* __restrict__ sstart, GridParams P,
+                                                        int cap, int* __restrict__ cnt) {
+    __shared__ u32 U[CQ_RMAX];
+    __shared__ u32 V[CQ_RMAX];
+    __shared__ int q_pt[CQ_TILE];       // queued points (index relative to R)
+    __shared__ int q_c[CQ_TILE];        // their partial counts
+    __shared__ int q_s[CQ_TILE];        // their strips
+    __shared__ int s_sA, s_sB, s_nq;
+    const int tid = threadIdx.x;
+    const int t0 = blockIdx.x * CQ_TILE;
+    const int t1 = min(t0 + CQ_TILE, P.n_act);
+    const int i = t0 + tid;
+    int s = 0;
+    if (i < t1) {
+        s = (int)((__ldg(keys + i) & KEY_MASK) >> P.sshift);
+        if (tid == 0) { s_sA = s; s_nq = 0; }
+        if (i == t1 - 1) s_sB = s;
+    }
+    __syncthreads();
+    const int r0 = __ldg(sstart + s_sA);          // first point of strip sA-1
+    const int r1 = __ldg(sstart + s_sB + 3);      // end of strip sB+1
+    if (r1 - r0 > CQ_RMAX) {                      // CTA-uniform
+        if (i < t1) cnt[i] = count_point_global(keys, sstart, P, cap, i);
+        return;
+    }
+    for (int j = r0 + tid; j < r1; j += CQ_TILE) {
+        const u64 k = __ldg(keys + j);
+        U[j - r0] = (u32)(k >> P.be) & P.umask;
+        V[j - r0] = (u32)k & P.emask;
+    }
+    __syncthreads();
+    // ---- phase 1: own strip.  Uniform trip counts: the in-window predicate is monotone along the sorted
+    // strip, so probing the cap-1 nearest points on each side gives min(count, cap-1) per side.
+    int c = 1;
+    bool need = false;
+    const int me = i - r0;
+    if (i < t1) {
+        const int lo_s = __ldg(sstart + s + 1) - r0, hi_s = __ldg(sstart + s + 2) - r0;
+        const u32 up = U[me];
+        const u32 ulo = up > (u32)P.eps ? up - (u32)P.eps : 0u;
+        const u64 h = (u64)up + (u64)P.eps;
+        const u32 uhi = h < (u64)P.umask ? (u32)h : P.umask;
+        if (cap <= 9) {
+            for (int k = 1; k < cap; ++k) {
+                const int jl = me - k, jr = me + k;
+                const bool okl = jl >= lo_s, okr = jr < hi_s;
+                const u32 ul = U[okl ? jl : me], ur = U[okr ? jr : me];
+                c += (okl && ul >= ulo) ? 1 : 0;
+                c += (okr && ur <= uhi) ? 1 : 0;
+            }
+        } else {
+            c = upper_bound_s(U, me + 1, hi_s, uhi) - lower_bound_s(U, lo_s, me, ulo);
+        }
+        need = c < cap;
+        if (!need) cnt[i] = cap;
+    }
+    // ---- compaction of the unsaturated points
+    {
+        const unsigned b = __ballot_sync(0xffffffffu, need);
+        const int lane = tid & 31;
+        int base = 0;
+        if (lane == 0 && b) base = atomicAdd(&s_nq, __popc(b));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (need) {
+            const int slot = base + __popc(b & ((1u << lane) - 1));
+            q_pt[slot] = me;
+            q_c[slot] = c;
+            q_s[slot] = s;
+        }
+    }
+    __syncthreads();
+    // ---- phase 2: strips s-1 and s+1
+    if (tid < s_nq) {
+        const int pm = q_pt[tid];
+        const int ps = q_s[tid];
+        c = q_c[tid];
+        const u32 up = U[pm], vm = V[pm];
+        const u32 ulo = up > (u32)P.eps ? up - (u32)P.eps : 0u;
+        const u64 h = (u64)up + (u64)P.eps;
+        const u32 uhi = h < (u64)P.umask ? (u32)h : P.umask;
+        const int a = __ldg(sstart + ps) - r0, lo_s = __ldg(sstart + ps + 1) - r0;
+        const int hi_s = __ldg(sstart + ps + 2) - r0, b = __ldg(sstart + ps + 3) - r0;
+        c = adjacent_strip_count<true>(U, V, a, lo_s, pm, ulo, uhi, vm, c, cap);
+        if (c < cap) c = adjacent_strip_count<false>(U, V, hi_s, b, pm, ulo, uhi, vm, c, cap);
+        cnt[r0 + pm] = c < cap ? c : cap;
+    }
 }
 
 static int bits_for(u64 v) {  // number of bits needed to represent values 0..v
@@ -236,7 +373,7 @@ int index_count(cloops_index* ix, int cap, int* d_counts_sorted, cudaStream_t st
     const GridParams& P = ix->P;
     if (P.n_act == 0) return 0;
     if (cap <= 0) cap = INT_MAX;
-    LAUNCH(count_kernel, cdiv(P.n_act, 256), 256, 0, st, ix->keys, ix->sstart, P, cap, d_counts_sorted);
+    LAUNCH(count_kernel, cdiv(P.n_act, CQ_TILE), CQ_TILE, 0, st, ix->keys, ix->sstart, P, cap, d_counts_sorted);
     return 0;
 }
 

@@ -13,33 +13,44 @@ __global__ void __launch_bounds__(256) summary_init_kernel(int* __restrict__ bbo
     size[c] = 0;
 }
 
-// Rows arrive in file order, so labels inside a warp are unrelated in general; a warp whose lanes all
-// carry the same label (giant Hi-C diagonal clusters) reduces in registers and issues one atomic set.
+// Rows arrive in file order, so labels inside a CTA are unrelated in general, and one giant cluster
+// (the Hi-C / self-ligation diagonal) can own half of all rows.  Each CTA therefore aggregates in a
+// small shared-memory cache (64 direct-mapped slots keyed by label); only the per-CTA partials and the
+// rare slot collisions reach the global atomics.
+#define SUM_SLOTS 64
 __global__ void __launch_bounds__(256) summary_accumulate_kernel(const int* __restrict__ x, const int* __restrict__ y,
                                                                  const int* __restrict__ labels, long long n, long long k,
                                                                  int* __restrict__ bbox, int* __restrict__ size) {
+    __shared__ int s_lab[SUM_SLOTS], s_x0[SUM_SLOTS], s_x1[SUM_SLOTS], s_y0[SUM_SLOTS], s_y1[SUM_SLOTS], s_cnt[SUM_SLOTS];
+    if (threadIdx.x < SUM_SLOTS) {
+        s_lab[threadIdx.x] = -1; s_cnt[threadIdx.x] = 0;
+        s_x0[threadIdx.x] = INT_MAX; s_x1[threadIdx.x] = INT_MIN; s_y0[threadIdx.x] = INT_MAX; s_y1[threadIdx.x] = INT_MIN;
+    }
+    __syncthreads();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     int lab = (i < n) ? __ldg(labels + i) : -1;
     if (lab >= k) lab = -1;
-    int xx = 0, yy = 0;
-    if (lab >= 0) { xx = __ldg(x + i); yy = __ldg(y + i); }
-    const unsigned full = 0xffffffffu;
-    int lab0 = __shfl_sync(full, lab, 0);
-    if (__all_sync(full, lab == lab0)) {
-        if (lab0 < 0) return;
-        int x0 = __reduce_min_sync(full, xx), x1 = __reduce_max_sync(full, xx);
-        int y0 = __reduce_min_sync(full, yy), y1 = __reduce_max_sync(full, yy);
-        if ((threadIdx.x & 31) == 0) {
-            int* b = bbox + 4LL * lab0;
-            atomicMin(b + 0, x0); atomicMax(b + 1, x1); atomicMin(b + 2, y0); atomicMax(b + 3, y1);
-            atomicAdd(size + lab0, 32);
+    if (lab >= 0) {
+        const int xx = __ldg(x + i), yy = __ldg(y + i);
+        const int slot = lab & (SUM_SLOTS - 1);
+        const int prev = atomicCAS(&s_lab[slot], -1, lab);
+        if (prev == -1 || prev == lab) {
+            atomicMin(&s_x0[slot], xx); atomicMax(&s_x1[slot], xx);
+            atomicMin(&s_y0[slot], yy); atomicMax(&s_y1[slot], yy);
+            atomicAdd(&s_cnt[slot], 1);
+        } else {
+            int* b = bbox + 4LL * lab;
+            atomicMin(b + 0, xx); atomicMax(b + 1, xx); atomicMin(b + 2, yy); atomicMax(b + 3, yy);
+            atomicAdd(size + lab, 1);
         }
-        return;
     }
-    if (lab < 0) return;
-    int* b = bbox + 4LL * lab;
-    atomicMin(b + 0, xx); atomicMax(b + 1, xx); atomicMin(b + 2, yy); atomicMax(b + 3, yy);
-    atomicAdd(size + lab, 1);
+    __syncthreads();
+    if (threadIdx.x < SUM_SLOTS && s_lab[threadIdx.x] >= 0) {
+        const int t = threadIdx.x;
+        int* b = bbox + 4LL * s_lab[t];
+        atomicMin(b + 0, s_x0[t]); atomicMax(b + 1, s_x1[t]); atomicMin(b + 2, s_y0[t]); atomicMax(b + 3, s_y1[t]);
+        atomicAdd(size + s_lab[t], s_cnt[t]);
+    }
 }
 
 __global__ void __launch_bounds__(256) summary_kind_kernel(const int* __restrict__ bbox, const int* __restrict__ size, long long k,
