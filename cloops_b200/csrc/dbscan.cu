@@ -64,7 +64,6 @@ __global__ void __launch_bounds__(256) flag_kernel(u64* __restrict__ keys, GridP
         u64 k = keys[i] & KEY_MASK;
         core = W.cnt[i] >= minPts;
         keys[i] = core ? (k | CORE_FLAG) : k;
-        W.parent[i] = i;
         W.rank[i] = INT_MAX;
         W.ncore[i] = 0;
         W.size[i] = 0;
@@ -114,10 +113,32 @@ __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
 }
 
 // Core graph edges.  Every core-core edge joins points of the same strip or of adjacent strips.
-//  * same strip: core points within eps in u form chains; linking each core point to its nearest core
-//    point on the left (if within eps) connects every chain.
-//  * strip s-1: inside the u-window at most two chains of strip s-1 are visible; one union per chain
-//    (with any member that passes the v test) is enough.
+//  * same strip: core points within eps in u form CHAINS (consecutive core points of the strip whose u
+//    gaps are <= eps).  A chain is one connected set, so it needs no union-find at all: a core point
+//    is a chain head iff it has no core point within eps on its left, and every core point's parent is
+//    the latest head at or before it -- one inclusive max-scan over the head indices.
+//  * strip s-1: inside the u-window at most two chains of strip s-1 are visible; one union per visible
+//    chain (through any member that passes the v test) is enough.  Only these cross-strip links go
+//    through the lock-free union-find, whose trees start out flat (depth 1).
+__global__ void __launch_bounds__(256) chain_head_kernel(const u64* __restrict__ keys, const int* __restrict__ sstart, GridParams P,
+                                                         int* __restrict__ head) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n_act) return;
+    const u64 key = keys[i];
+    int h = 0;
+    if (key >> 63) {
+        const PointView p = view(key, P);
+        const int lo_s = __ldg(sstart + p.s + 1);
+        h = i;
+        for (int j = i - 1; j >= lo_s; --j) {
+            u64 kq = keys[j];
+            if (((u32)(kq >> P.be) & P.umask) < p.ulo) break;
+            if (kq >> 63) { h = 0; break; }
+        }
+    }
+    head[i] = h;
+}
+
 __global__ void __launch_bounds__(256) union_kernel(const u64* __restrict__ keys, const int* __restrict__ sstart, GridParams P,
                                                     int* __restrict__ parent) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -126,11 +147,6 @@ __global__ void __launch_bounds__(256) union_kernel(const u64* __restrict__ keys
     if (!(key >> 63)) return;
     const PointView p = view(key, P);
     const int lo_s = __ldg(sstart + p.s + 1);
-    for (int j = i - 1; j >= lo_s; --j) {
-        u64 kq = keys[j];
-        if (((u32)(kq >> P.be) & P.umask) < p.ulo) break;
-        if (kq >> 63) { uf_union(parent, i, j); break; }
-    }
     const int a = __ldg(sstart + p.s);
     if (a < lo_s) {
         u64 base = (u64)(p.s - 1) << P.bu;
@@ -202,11 +218,15 @@ __global__ void __launch_bounds__(256) v1_border_kernel(const u64* __restrict__ 
     W.assigned[i] = best_seed_root >= 0 ? best_seed_root : best_any_root;
 }
 
+// members per root (v1's "< minPts members" deletion).  Index order is spatially coherent: lanes are
+// grouped by root first, so the giant diagonal cluster costs one atomic per warp, not one per point.
 __global__ void __launch_bounds__(256) size_kernel(GridParams P, Work W) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.n_act) return;
-    int a = W.assigned[i];
-    if (a >= 0) atomicAdd(&W.size[a], 1);
+    const int a = (i < P.n_act) ? W.assigned[i] : -1;
+    const unsigned am = __ballot_sync(0xffffffffu, a >= 0);
+    if (a < 0) return;
+    const unsigned m = __match_any_sync(am, a);
+    if ((int)(threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(&W.size[a], __popc(m));
 }
 
 // ---- v2 survival ------------------------------------------------------------------------------------
@@ -377,7 +397,18 @@ int index_dbscan(cloops_index* ix, int minPts, int variant, int* d_labels, int64
         LAUNCH(cellmin_kernel, g, 256, 0, st, ix->rows, P, W);
     }
     stage_mark("flags_cells", st);
-    LAUNCH(union_kernel, g, 256, 0, st, ix->keys, ix->sstart, P, W.parent);
+    {
+        // chains inside strips by scan (parent = latest chain head), cross-strip links by union-find
+        int* head = W.assigned;                    // scratch: assigned[] is written later by compress_kernel
+        LAUNCH(chain_head_kernel, g, 256, 0, st, ix->keys, ix->sstart, P, head);
+        size_t scan_bytes = 0;
+        CU_TRY(cub::DeviceScan::InclusiveScan(nullptr, scan_bytes, head, W.parent, cub::Max(), na, st));
+        void* d_scan;
+        RET_IF(tmp.alloc((char**)&d_scan, scan_bytes));
+        CU_TRY(cub::DeviceScan::InclusiveScan(d_scan, scan_bytes, head, W.parent, cub::Max(), na, st));
+        stage_mark("chains", st);
+        LAUNCH(union_kernel, g, 256, 0, st, ix->keys, ix->sstart, P, W.parent);
+    }
     stage_mark("union", st);
     LAUNCH(compress_kernel, g, 256, 0, st, ix->keys, ix->rows, P, W, variant);
     stage_mark("compress", st);

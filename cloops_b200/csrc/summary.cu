@@ -30,18 +30,26 @@ __global__ void __launch_bounds__(256) summary_accumulate_kernel(const int* __re
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     int lab = (i < n) ? __ldg(labels + i) : -1;
     if (lab >= k) lab = -1;
+    const unsigned lm = __ballot_sync(0xffffffffu, lab >= 0);
     if (lab >= 0) {
-        const int xx = __ldg(x + i), yy = __ldg(y + i);
-        const int slot = lab & (SUM_SLOTS - 1);
-        const int prev = atomicCAS(&s_lab[slot], -1, lab);
-        if (prev == -1 || prev == lab) {
-            atomicMin(&s_x0[slot], xx); atomicMax(&s_x1[slot], xx);
-            atomicMin(&s_y0[slot], yy); atomicMax(&s_y1[slot], yy);
-            atomicAdd(&s_cnt[slot], 1);
-        } else {
-            int* b = bbox + 4LL * lab;
-            atomicMin(b + 0, xx); atomicMax(b + 1, xx); atomicMin(b + 2, yy); atomicMax(b + 3, yy);
-            atomicAdd(size + lab, 1);
+        int xx = __ldg(x + i), yy = __ldg(y + i);
+        // lanes of the warp that carry the same label reduce in registers; one lane speaks for the group
+        const unsigned m = __match_any_sync(lm, lab);
+        const int x0 = __reduce_min_sync(m, xx), x1 = __reduce_max_sync(m, xx);
+        const int y0 = __reduce_min_sync(m, yy), y1 = __reduce_max_sync(m, yy);
+        if ((int)(threadIdx.x & 31) == __ffs(m) - 1) {
+            const int cntm = __popc(m);
+            const int slot = lab & (SUM_SLOTS - 1);
+            const int prev = atomicCAS(&s_lab[slot], -1, lab);
+            if (prev == -1 || prev == lab) {
+                atomicMin(&s_x0[slot], x0); atomicMax(&s_x1[slot], x1);
+                atomicMin(&s_y0[slot], y0); atomicMax(&s_y1[slot], y1);
+                atomicAdd(&s_cnt[slot], cntm);
+            } else {
+                int* b = bbox + 4LL * lab;
+                atomicMin(b + 0, x0); atomicMax(b + 1, x1); atomicMin(b + 2, y0); atomicMax(b + 3, y1);
+                atomicAdd(size + lab, cntm);
+            }
         }
     }
     __syncthreads();
