@@ -223,11 +223,6 @@ def main():
     L.cloops_set_profiling(1)
     rq_ms, stage_tot = [], {}
 
-    def step_dev_prof():
-        r = hotpath.run_device(dx, dy, EPS, MINPTS, score=False)
-        st = _lib.stage_times()          # stages of the last library call = cluster_summary; dbscan stages read below
-        return r
-
     barrier()
     sampler = ClockSampler(visible_index(local))
     sampler.start()
@@ -261,7 +256,10 @@ def main():
         t = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)
         td.all_reduce(t, op=td.ReduceOp.MAX)
         t_dev, t_e2e = float(t[0]), float(t[1])
+    if world > 1:
+        td.barrier()
     if rank != 0:
+        dist.shutdown()
         return
     r = res["r"]
     n_act = r.info["n_active"]
@@ -294,6 +292,7 @@ def main():
         line["cpu_baseline"] = {"value": len(xs) / dt, "unit": "PETs/s", "cores": 1, "kind": "port",
                                 "sample": "PETs with X < 3%% of the chromosome (same density): %d PETs, %.1f s" % (len(xs), dt)}
     print(json.dumps(line), flush=True)
+    dist.shutdown()
 
 
 if __name__ == "__main__":

@@ -14,50 +14,56 @@ __global__ void __launch_bounds__(256) summary_init_kernel(int* __restrict__ bbo
 }
 
 // Rows arrive in file order, so labels inside a CTA are unrelated in general, and one giant cluster
-// (the Hi-C / self-ligation diagonal) can own half of all rows.  Each CTA therefore aggregates in a
-// small shared-memory cache (64 direct-mapped slots keyed by label); only the per-CTA partials and the
-// rare slot collisions reach the global atomics.
-#define SUM_SLOTS 64
+// (the Hi-C / self-ligation diagonal) can own half of all rows.  Lanes of a warp that carry the same
+// label first reduce in registers; the group leaders then aggregate in a CTA-wide open-addressing hash
+// table in shared memory (1024 slots for the at most 1024 rows a CTA visits; a probe sequence longer
+// than 64 falls back to global atomics); only one partial per (CTA, label) reaches the global atomics.
+#define SUM_SLOTS 1024
+#define SUM_TILES 4
 __global__ void __launch_bounds__(256) summary_accumulate_kernel(const int* __restrict__ x, const int* __restrict__ y,
                                                                  const int* __restrict__ labels, long long n, long long k,
                                                                  int* __restrict__ bbox, int* __restrict__ size) {
     __shared__ int s_lab[SUM_SLOTS], s_x0[SUM_SLOTS], s_x1[SUM_SLOTS], s_y0[SUM_SLOTS], s_y1[SUM_SLOTS], s_cnt[SUM_SLOTS];
-    if (threadIdx.x < SUM_SLOTS) {
-        s_lab[threadIdx.x] = -1; s_cnt[threadIdx.x] = 0;
-        s_x0[threadIdx.x] = INT_MAX; s_x1[threadIdx.x] = INT_MIN; s_y0[threadIdx.x] = INT_MAX; s_y1[threadIdx.x] = INT_MIN;
+    for (int t = threadIdx.x; t < SUM_SLOTS; t += blockDim.x) {
+        s_lab[t] = -1; s_cnt[t] = 0;
+        s_x0[t] = INT_MAX; s_x1[t] = INT_MIN; s_y0[t] = INT_MAX; s_y1[t] = INT_MIN;
     }
     __syncthreads();
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    int lab = (i < n) ? __ldg(labels + i) : -1;
-    if (lab >= k) lab = -1;
-    const unsigned lm = __ballot_sync(0xffffffffu, lab >= 0);
-    if (lab >= 0) {
+    for (int tile = 0; tile < SUM_TILES; ++tile) {
+        long long i = ((long long)blockIdx.x * SUM_TILES + tile) * blockDim.x + threadIdx.x;
+        int lab = (i < n) ? __ldg(labels + i) : -1;
+        if (lab >= k) lab = -1;
+        const unsigned lm = __ballot_sync(0xffffffffu, lab >= 0);
+        if (lab < 0) continue;
         int xx = __ldg(x + i), yy = __ldg(y + i);
-        // lanes of the warp that carry the same label reduce in registers; one lane speaks for the group
         const unsigned m = __match_any_sync(lm, lab);
         const int x0 = __reduce_min_sync(m, xx), x1 = __reduce_max_sync(m, xx);
         const int y0 = __reduce_min_sync(m, yy), y1 = __reduce_max_sync(m, yy);
-        if ((int)(threadIdx.x & 31) == __ffs(m) - 1) {
-            const int cntm = __popc(m);
-            const int slot = lab & (SUM_SLOTS - 1);
+        if ((int)(threadIdx.x & 31) != __ffs(m) - 1) continue;
+        int slot = (int)(((unsigned)lab * 2654435761u) >> 22);            // 10 bits
+        bool found = false;
+        for (int probe = 0; probe < 64; ++probe) {
             const int prev = atomicCAS(&s_lab[slot], -1, lab);
-            if (prev == -1 || prev == lab) {
-                atomicMin(&s_x0[slot], x0); atomicMax(&s_x1[slot], x1);
-                atomicMin(&s_y0[slot], y0); atomicMax(&s_y1[slot], y1);
-                atomicAdd(&s_cnt[slot], cntm);
-            } else {
-                int* b = bbox + 4LL * lab;
-                atomicMin(b + 0, x0); atomicMax(b + 1, x1); atomicMin(b + 2, y0); atomicMax(b + 3, y1);
-                atomicAdd(size + lab, cntm);
-            }
+            if (prev == -1 || prev == lab) { found = true; break; }
+            slot = (slot + 1) & (SUM_SLOTS - 1);
+        }
+        if (found) {
+            atomicMin(&s_x0[slot], x0); atomicMax(&s_x1[slot], x1);
+            atomicMin(&s_y0[slot], y0); atomicMax(&s_y1[slot], y1);
+            atomicAdd(&s_cnt[slot], __popc(m));
+        } else {
+            int* b = bbox + 4LL * lab;
+            atomicMin(b + 0, x0); atomicMax(b + 1, x1); atomicMin(b + 2, y0); atomicMax(b + 3, y1);
+            atomicAdd(size + lab, __popc(m));
         }
     }
     __syncthreads();
-    if (threadIdx.x < SUM_SLOTS && s_lab[threadIdx.x] >= 0) {
-        const int t = threadIdx.x;
-        int* b = bbox + 4LL * s_lab[t];
+    for (int t = threadIdx.x; t < SUM_SLOTS; t += blockDim.x) {
+        const int l = s_lab[t];
+        if (l < 0) continue;
+        int* b = bbox + 4LL * l;
         atomicMin(b + 0, s_x0[t]); atomicMax(b + 1, s_x1[t]); atomicMin(b + 2, s_y0[t]); atomicMax(b + 3, s_y1[t]);
-        atomicAdd(size + s_lab[t], s_cnt[t]);
+        atomicAdd(size + l, s_cnt[t]);
     }
 }
 
@@ -86,7 +92,7 @@ int cluster_summary(const int32_t* d_x, const int32_t* d_y, const int32_t* d_lab
     if (n < 0 || k < 0) return fail(CLOOPS_EINVAL, "negative size");
     if (k > 0) LAUNCH(summary_init_kernel, cdiv(k, 256), 256, 0, st, d_bbox, d_size, (long long)k);
     if (n > 0 && k > 0)
-        LAUNCH(summary_accumulate_kernel, cdiv(n, 256), 256, 0, st, d_x, d_y, d_labels, (long long)n, (long long)k, d_bbox, d_size);
+        LAUNCH(summary_accumulate_kernel, cdiv(n, 256 * SUM_TILES), 256, 0, st, d_x, d_y, d_labels, (long long)n, (long long)k, d_bbox, d_size);
     if (k > 0) LAUNCH(summary_kind_kernel, cdiv(k, 256), 256, 0, st, d_bbox, d_size, (long long)k, d_kind);
     if (n > 0 && d_row_kind) {
         if (k > 0) LAUNCH(summary_rowkind_kernel, cdiv(n, 256), 256, 0, st, d_labels, d_kind, (long long)n, (long long)k, d_row_kind);

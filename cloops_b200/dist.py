@@ -24,11 +24,14 @@ def init_from_env(backend: str | None = None) -> None:
     local = int(os.environ.get("LOCAL_RANK", str(rank)))
     if backend is None:
         backend = "nccl" if torch.cuda.is_available() else "gloo"
+    kwargs = {}
     if torch.cuda.is_available():
         torch.cuda.set_device(local % torch.cuda.device_count())
+        if backend == "nccl":
+            kwargs["device_id"] = torch.device("cuda", local % torch.cuda.device_count())
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     if not td.is_initialized():
-        td.init_process_group(backend=backend, rank=rank, world_size=world)
+        td.init_process_group(backend=backend, rank=rank, world_size=world, **kwargs)
     _state.update(rank=rank, world=world, init=True)
 
 
@@ -91,3 +94,12 @@ def barrier() -> None:
     if world() > 1:
         import torch.distributed as td
         td.barrier()
+
+
+def shutdown() -> None:
+    """Leave the process group (quietens NCCL's exit warning)."""
+    if _state["init"]:
+        import torch.distributed as td
+        if td.is_initialized():
+            td.destroy_process_group()
+        _state.update(rank=0, world=1, init=False)

@@ -246,6 +246,7 @@ def main(argv=None):
     dist.init_from_env()
     pipe(op.fnIn.split(","), op.fnOut, eps, minPts, op.chroms, op.cpu, op.tmp, hic, op.washU, op.juice, op.cut,
          op.plot, op.max_cut)
+    dist.shutdown()
     logger.info("cLoops finished. Used CPU time: %s Bye!\n\n\n" % (datetime.now() - start))
 
 

@@ -85,3 +85,23 @@ def test_getintsig_matches_reference_tuples(need_gpu, gold_dir, tmp_path):
     # host-side getCounts keeps the reference's set-of-row-indices contract
     X = d["X"].astype(np.int64)
     assert cModel.getCounts([41000000, 41010000], model[0]) == set(np.flatnonzero((X >= 41000000) & (X <= 41010000)).tolist())
+
+
+def test_pipe_multi_chrom_hic(need_gpu, gold_dir, tmp_path, monkeypatch):
+    """3 chromosomes, 2 eps x 2 minPts rounds, -hic marks: byte-identical to the reference's .loop
+    (tests/golden/multi_hic.*, written by oracle/make_golden_multi.py)."""
+    from cloops_b200 import pipe
+    gold = np.load(os.path.join(gold_dir, "multi_hic.npz"))
+    bedpe = str(tmp_path / "in.bedpe")
+    with open(bedpe, "w") as fh:
+        for name in ("chr1", "chr2", "chrX"):
+            for x, y in zip(gold[name + "_X"].tolist(), gold[name + "_Y"].tolist()):
+                fh.write("%s\t%d\t%d\t%s\t%d\t%d\tp\t.\t+\t-\n" % (name, x, x, name, y, y))
+    monkeypatch.chdir(tmp_path)
+    cuts = []
+    orig = pipe.estIntSelCutFrag
+    monkeypatch.setattr(pipe, "estIntSelCutFrag", lambda di, ds, log=1: (cuts.append((len(di), len(ds), orig(di, ds, log)[0])), orig(di, ds, log))[1])
+    pipe.pipe([bedpe], "out", [1000, 2000], [8, 5], cpu=1, tmp=0, hic=1)
+    assert np.array_equal(np.array(cuts, np.int64), gold["cuts"])
+    assert open(tmp_path / "out.loop", "rb").read() == open(os.path.join(gold_dir, "multi_hic.loop"), "rb").read()
+    assert not os.path.isdir(tmp_path / "out")       # temp .jd directory removed without -s
