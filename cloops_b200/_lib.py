@@ -35,7 +35,9 @@ _SIGNATURES = {
     "cloops_index_free": (None, [_vp]),
     "cloops_index_n_active": (_i64, [_vp]),
     "cloops_index_count": (C.c_int, [_vp, _i32, _vp, _vp]),
-    "cloops_index_dbscan": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp]),
+    "cloops_index_dbscan": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "cloops_index_coords": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "cloops_row_kinds": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp]),
     "cloops_cluster_summary": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "cloops_coverage_build": (C.c_int, [_vp, _vp, _i64, C.POINTER(_vp), _vp]),
     "cloops_coverage_free": (None, [_vp]),

@@ -4,7 +4,8 @@
 #include "index.cuh"
 
 namespace cloops {
-int index_dbscan(cloops_index* ix, int minPts, int variant, int* d_labels, int64_t* h_info, cudaStream_t st);
+int index_dbscan(cloops_index* ix, int minPts, int variant, int* d_labels, int* d_labels_sorted, int64_t* h_info, cudaStream_t st);
+int row_kinds(const int32_t* d_labels, int64_t n, const uint8_t* d_kind, int64_t k, uint8_t* d_row_kind, cudaStream_t st);
 int block_dbscan(const int32_t* d_x, const int32_t* d_y, int64_t n, int32_t eps, int32_t minPts, int32_t cut, int32_t* d_labels,
                  int64_t* h_info, cudaStream_t st);
 int cluster_summary(const int32_t* d_x, const int32_t* d_y, const int32_t* d_labels, int64_t n, int64_t k, int32_t* d_bbox,
@@ -61,12 +62,22 @@ int cloops_index_count(cloops_index* ix, int32_t cap, int32_t* d_counts_sorted, 
     return index_count(ix, cap, d_counts_sorted, (cudaStream_t)stream);
 }
 
-int cloops_index_dbscan(cloops_index* ix, int32_t minPts, int32_t variant, int32_t* d_labels, int64_t* h_info, void* stream) {
+int cloops_index_dbscan(cloops_index* ix, int32_t minPts, int32_t variant, int32_t* d_labels, int32_t* d_labels_sorted,
+                        int64_t* h_info, void* stream) {
     if (!ix) return fail(CLOOPS_EINVAL, "index is NULL");
     cudaStream_t st = (cudaStream_t)stream;
     stages_begin(st);
-    RET_IF(index_dbscan(ix, minPts, variant, d_labels, h_info, st));
+    RET_IF(index_dbscan(ix, minPts, variant, d_labels, d_labels_sorted, h_info, st));
     return stages_end(st);
+}
+
+int cloops_index_coords(cloops_index* ix, int32_t* d_xs, int32_t* d_ys, void* stream) {
+    if (!ix) return fail(CLOOPS_EINVAL, "index is NULL");
+    return index_coords(ix, d_xs, d_ys, (cudaStream_t)stream);
+}
+
+int cloops_row_kinds(const int32_t* d_labels, int64_t n, const uint8_t* d_kind, int64_t n_clusters, uint8_t* d_row_kind, void* stream) {
+    return row_kinds(d_labels, n, d_kind, n_clusters, d_row_kind, (cudaStream_t)stream);
 }
 
 int cloops_dbscan(const int32_t* d_x, const int32_t* d_y, int64_t n, int32_t eps, int32_t minPts, int32_t cut, int32_t variant,
@@ -82,7 +93,7 @@ int cloops_dbscan(const int32_t* d_x, const int32_t* d_y, int64_t n, int32_t eps
     stages_begin(st);
     cloops_index* ix = nullptr;
     int rc = index_build(d_x, d_y, n, eps, cut, &ix, st);
-    if (rc == 0) rc = index_dbscan(ix, minPts, variant, d_labels, h_info, st);
+    if (rc == 0) rc = index_dbscan(ix, minPts, variant, d_labels, nullptr, h_info, st);
     index_free(ix, st);
     if (rc != 0) return rc;
     return stages_end(st);

@@ -28,8 +28,9 @@ namespace cloops {
 
 struct Windows {
     int a0[NW], a1[NW], b0[NW], b1[NW];
-    int h0[2], h1[2];    // disjoint hull intervals
+    int h0[2], h1[2];    // disjoint hull intervals (merged when the two families overlap)
     int nh;
+    int fa0, fa1, fb0, fb1;   // hull of the A family / of the B family (anchor included)
 };
 
 __device__ __forceinline__ long long fdiv2(long long a) { return (a >= 0) ? a / 2 : -((-a + 1) / 2); }  // floor(a/2)
@@ -56,6 +57,7 @@ __device__ void make_windows(int iva0, int iva1, int ivb0, int ivb1, int win, Wi
         ha0 = min(ha0, W.a0[w]); ha1 = max(ha1, W.a1[w]);
         hb0 = min(hb0, W.b0[w]); hb1 = max(hb1, W.b1[w]);
     }
+    W.fa0 = ha0; W.fa1 = ha1; W.fb0 = hb0; W.fb1 = hb1;
     if (ha0 > hb0) { int t = ha0; ha0 = hb0; hb0 = t; t = ha1; ha1 = hb1; hb1 = t; }
     if (hb0 <= ha1) { W.nh = 1; W.h0[0] = ha0; W.h1[0] = max(ha1, hb1); }
     else { W.nh = 2; W.h0[0] = ha0; W.h1[0] = ha1; W.h0[1] = hb0; W.h1[1] = hb1; }
@@ -110,13 +112,24 @@ __global__ void __launch_bounds__(128) range_count_kernel(const int* __restrict_
                 for (int g = 0; g < nh; ++g) seen |= (x >= W.h0[g] && x <= W.h1[g]);
                 if (seen) continue;
             }
+            // a coordinate can only fall into a window of a family whose hull contains it: the X-sorted
+            // slice is inside one hull by construction, and the partner coordinate is usually far away
             unsigned ma = 0, mb = 0;
+            const bool xa = x >= W.fa0 && x <= W.fa1, ya = y >= W.fa0 && y <= W.fa1;
+            const bool xb = x >= W.fb0 && x <= W.fb1, yb = y >= W.fb0 && y <= W.fb1;
+            if (xa || ya) {
 #pragma unroll
-            for (int w = 0; w < NWIN; ++w) {
-                bool ina = (x >= W.a0[w] && x <= W.a1[w]) || (y >= W.a0[w] && y <= W.a1[w]);
-                bool inb = (x >= W.b0[w] && x <= W.b1[w]) || (y >= W.b0[w] && y <= W.b1[w]);
-                ma |= (ina ? 1u : 0u) << w;
-                mb |= (inb ? 1u : 0u) << w;
+                for (int w = 0; w < NWIN; ++w) {
+                    const int lo = W.a0[w], hi = W.a1[w];
+                    ma |= (((x >= lo && x <= hi) || (y >= lo && y <= hi)) ? 1u : 0u) << w;
+                }
+            }
+            if (xb || yb) {
+#pragma unroll
+                for (int w = 0; w < NWIN; ++w) {
+                    const int lo = W.b0[w], hi = W.b1[w];
+                    mb |= (((x >= lo && x <= hi) || (y >= lo && y <= hi)) ? 1u : 0u) << w;
+                }
             }
             if ((ma | mb) == 0) continue;
             if (ma & 1u) atomicAdd(&acc[0], 1);

@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(256) number_flags_kernel(const u64* __restrict
 }
 
 __global__ void __launch_bounds__(256) label_kernel(const u32* __restrict__ rows, GridParams P, Work W, int variant, int minPts,
-                                                    int* __restrict__ labels) {
+                                                    int* __restrict__ labels, int* __restrict__ labels_sorted) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int lab = -1;
     if (i < P.n_act) {
@@ -346,11 +346,12 @@ __global__ void __launch_bounds__(256) label_kernel(const u32* __restrict__ rows
             if (keep) lab = W.ids[W.rank[a]];
         }
         labels[rows[i]] = lab;
+        if (labels_sorted) labels_sorted[i] = lab;
     }
     block_count(W.slots_lab, lab >= 0);
 }
 
-int index_dbscan(cloops_index* ix, int minPts, int variant, int* d_labels, int64_t* h_info, cudaStream_t st) {
+int index_dbscan(cloops_index* ix, int minPts, int variant, int* d_labels, int* d_labels_sorted, int64_t* h_info, cudaStream_t st) {
     const GridParams& P = ix->P;
     if (minPts < 1) return fail(CLOOPS_EINVAL, "minPts must be >= 1 (got %d)", minPts);
     if (variant != CLOOPS_V1 && variant != CLOOPS_V2) return fail(CLOOPS_EINVAL, "variant %d not served by the strip index", variant);
@@ -448,7 +449,7 @@ int index_dbscan(cloops_index* ix, int minPts, int variant, int* d_labels, int64
         RET_IF(tmp.alloc((char**)&d_scan, scan_bytes));
         CU_TRY(cub::DeviceScan::ExclusiveSum(d_scan, scan_bytes, W.flags, W.ids, P.n + 1, st));
     }
-    LAUNCH(label_kernel, g, 256, 0, st, ix->rows, P, W, variant, minPts, d_labels);
+    LAUNCH(label_kernel, g, 256, 0, st, ix->rows, P, W, variant, minPts, d_labels, d_labels_sorted);
     stage_mark("labels", st);
     if (h_info) {
         int n_clusters = 0;

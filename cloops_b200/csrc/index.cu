@@ -272,6 +272,24 @@ __global__ void __launch_bounds__(CQ_TILE) count_kernel(const u64* __restrict__ 
     }
 }
 
+// (X, Y) of every active PET in index order, decoded from the packed keys
+__global__ void __launch_bounds__(256) coords_kernel(const u64* __restrict__ keys, GridParams P, int* __restrict__ xs, int* __restrict__ ys) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n_act) return;
+    const u64 k = keys[i] & KEY_MASK;
+    const long long u = (long long)((u32)(k >> P.be) & P.umask) + P.ubase;
+    const long long v = (long long)(k >> P.sshift) * P.eps + ((u32)k & P.emask) + P.vbase;
+    xs[i] = (int)((u + v) >> 1);
+    ys[i] = (int)((v - u) >> 1);
+}
+
+int index_coords(cloops_index* ix, int* d_xs, int* d_ys, cudaStream_t st) {
+    const GridParams& P = ix->P;
+    if (P.n_act == 0) return 0;
+    LAUNCH(coords_kernel, cdiv(P.n_act, 256), 256, 0, st, ix->keys, P, d_xs, d_ys);
+    return 0;
+}
+
 static int bits_for(u64 v) {  // number of bits needed to represent values 0..v
     int b = 0;
     while (v) { ++b; v >>= 1; }

@@ -95,5 +95,6 @@ int index_build(const int32_t* d_x, const int32_t* d_y, int64_t n, int32_t eps, 
                 cudaStream_t st);
 void index_free(cloops_index* ix, cudaStream_t st);
 int index_count(cloops_index* ix, int cap, int* d_counts_sorted, cudaStream_t st);
+int index_coords(cloops_index* ix, int* d_xs, int* d_ys, cudaStream_t st);
 
 }  // namespace cloops

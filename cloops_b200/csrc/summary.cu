@@ -101,4 +101,11 @@ int cluster_summary(const int32_t* d_x, const int32_t* d_y, const int32_t* d_lab
     return 0;
 }
 
+int row_kinds(const int32_t* d_labels, int64_t n, const uint8_t* d_kind, int64_t k, uint8_t* d_row_kind, cudaStream_t st) {
+    if (n <= 0) return 0;
+    if (k > 0) LAUNCH(summary_rowkind_kernel, cdiv(n, 256), 256, 0, st, d_labels, d_kind, (long long)n, (long long)k, d_row_kind);
+    else CU_TRY(cudaMemsetAsync(d_row_kind, 0, n, st));
+    return 0;
+}
+
 }  // namespace cloops

@@ -10,6 +10,7 @@ from . import _lib
 from ._lib import CloopsError, check
 
 COORD_LIMIT = 1 << 30
+INFO_KEYS = ("n_active", "n_clusters", "n_components", "n_core", "n_dead", "n_strips", "key_bits", "n_labelled")
 
 
 def require_cuda() -> torch.device:
@@ -48,8 +49,7 @@ def dbscan_device(dx: torch.Tensor, dy: torch.Tensor, eps: int, minPts: int, var
     info = (C.c_int64 * 8)()
     check(_lib.lib().cloops_dbscan(dx.data_ptr(), dy.data_ptr(), n, int(eps), int(minPts), int(cut), int(variant),
                                    labels.data_ptr(), C.addressof(info), _stream()))
-    keys = ("n_active", "n_clusters", "n_components", "n_core", "n_dead", "n_strips", "key_bits", "n_labelled")
-    return labels, dict(zip(keys, (int(v) for v in info)))
+    return labels, dict(zip(INFO_KEYS, (int(v) for v in info)))
 
 
 def neighbour_counts_device(dx, dy, eps: int, cap: int = 0, cut: int = 0) -> torch.Tensor:
@@ -59,18 +59,46 @@ def neighbour_counts_device(dx, dy, eps: int, cap: int = 0, cut: int = 0) -> tor
     return out
 
 
-def cluster_summary_device(dx, dy, labels, n_clusters: int):
-    """bbox int32[K,4], size int32[K], kind uint8[K], row_kind uint8[n] (all CUDA tensors)."""
+def cluster_summary_device(dx, dy, labels, n_clusters: int, want_row_kind: bool = True):
+    """bbox int32[K,4], size int32[K], kind uint8[K], row_kind uint8[n] (all CUDA tensors).  The three
+    input arrays may be in any common order (row order or index order)."""
     n = dx.numel()
     k = int(n_clusters)
     dev = dx.device
     bbox = torch.empty((max(k, 1), 4), dtype=torch.int32, device=dev)
     size = torch.empty(max(k, 1), dtype=torch.int32, device=dev)
     kind = torch.empty(max(k, 1), dtype=torch.uint8, device=dev)
-    row_kind = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+    row_kind = torch.empty(max(n, 1), dtype=torch.uint8, device=dev) if want_row_kind else None
     check(_lib.lib().cloops_cluster_summary(dx.data_ptr(), dy.data_ptr(), labels.data_ptr(), n, k, bbox.data_ptr(),
-                                            size.data_ptr(), kind.data_ptr(), row_kind.data_ptr(), _stream()))
-    return bbox[:k], size[:k], kind[:k], row_kind[:n]
+                                            size.data_ptr(), kind.data_ptr(), row_kind.data_ptr() if want_row_kind else None, _stream()))
+    return bbox[:k], size[:k], kind[:k], (row_kind[:n] if want_row_kind else None)
+
+
+def row_kinds_device(labels, kind) -> torch.Tensor:
+    n, k = labels.numel(), kind.numel()
+    out = torch.empty(max(n, 1), dtype=torch.uint8, device=labels.device)
+    check(_lib.lib().cloops_row_kinds(labels.data_ptr(), n, kind.data_ptr(), k, out.data_ptr(), _stream()))
+    return out[:n]
+
+
+def cluster_and_summarise(dx, dy, eps: int, minPts: int, variant: int, cut: int = 0):
+    """labels (row order), info, bbox, size, kind, row_kind.  For v1/v2 the per-cluster reduction runs
+    in index order (spatially coherent: few distinct labels per warp), through the resident index."""
+    if variant == _lib.BLOCK:
+        labels, info = dbscan_device(dx, dy, eps, minPts, variant, cut)
+        return (labels, info) + tuple(cluster_summary_device(dx, dy, labels, info["n_clusters"]))
+    ix = Index(dx, dy, eps, cut)
+    try:
+        labels, ls, info = ix.dbscan(minPts, variant, want_sorted=True)
+        if ix.n_active:
+            xs, ys = ix.coords()
+            bbox, size, kind, _ = cluster_summary_device(xs, ys, ls, info["n_clusters"], want_row_kind=False)
+        else:
+            bbox, size, kind, _ = cluster_summary_device(dx, dy, labels, 0, want_row_kind=False)
+        row_kind = row_kinds_device(labels, kind)
+    finally:
+        ix.close()
+    return labels, info, bbox, size, kind, row_kind
 
 
 class Index:
@@ -90,11 +118,22 @@ class Index:
         check(_lib.lib().cloops_index_count(self._h, int(cap), out.data_ptr(), _stream()))
         return out
 
-    def dbscan(self, minPts: int, variant: int):
+    def dbscan(self, minPts: int, variant: int, want_sorted: bool = False):
+        """labels (row order) [+ labels in index order] + info dict."""
         labels = torch.empty(self.n, dtype=torch.int32, device=self._dx.device)
+        ls = torch.empty(max(self.n_active, 1), dtype=torch.int32, device=self._dx.device) if want_sorted else None
         info = (C.c_int64 * 8)()
-        check(_lib.lib().cloops_index_dbscan(self._h, int(minPts), int(variant), labels.data_ptr(), C.addressof(info), _stream()))
-        return labels, [int(v) for v in info]
+        check(_lib.lib().cloops_index_dbscan(self._h, int(minPts), int(variant), labels.data_ptr(),
+                                             ls.data_ptr() if want_sorted else None, C.addressof(info), _stream()))
+        info = dict(zip(INFO_KEYS, (int(v) for v in info)))
+        return (labels, ls[:self.n_active], info) if want_sorted else (labels, info)
+
+    def coords(self):
+        """(X, Y) of the active PETs in index order."""
+        xs = torch.empty(max(self.n_active, 1), dtype=torch.int32, device=self._dx.device)
+        ys = torch.empty_like(xs)
+        check(_lib.lib().cloops_index_coords(self._h, xs.data_ptr(), ys.data_ptr(), _stream()))
+        return xs[:self.n_active], ys[:self.n_active]
 
     def close(self):
         if getattr(self, "_h", None):

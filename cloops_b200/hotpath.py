@@ -21,8 +21,7 @@ def run_device(dx: torch.Tensor, dy: torch.Tensor, eps: int, minPts: int, varian
     """Inputs and outputs resident in HBM.  ``counts`` is int32 [n_inter, 123] for the inter-ligation
     candidates in ascending cluster-id order (cLoops/pipe.py:97, cModel.py:281-295)."""
     r = HotPathResult()
-    r.labels, r.info = device.dbscan_device(dx, dy, eps, minPts, variant, cut)
-    r.bbox, r.size, r.kind, r.row_kind = device.cluster_summary_device(dx, dy, r.labels, r.info["n_clusters"])
+    r.labels, r.info, r.bbox, r.size, r.kind, r.row_kind = device.cluster_and_summarise(dx, dy, eps, minPts, variant, cut)
     r.cand = r.counts = None
     if score:
         cand = r.bbox[r.kind == 1].clamp_(min=0)[:, [0, 1, 2, 3]].contiguous()     # max(0, .) of cModel.py:281-282

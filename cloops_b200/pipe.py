@@ -73,8 +73,8 @@ def singleDBSCAN(f, eps, minPts, cut=0):
         return key, f, dataI, dataS, dis, dss
     sys.stderr.write("Clustering %s and %s using eps as %s, minPts as %s,pre-set distance cutoff as > %s\n" %
                      (key[0], key[1], eps, minPts, cut))
-    labels, info = device.dbscan_device(ch.dx, ch.dy, int(eps), int(minPts), DBSCAN_VARIANT, int(cut) if cut > 0 else 0)
-    bbox, size, kind, row_kind = device.cluster_summary_device(ch.dx, ch.dy, labels, info["n_clusters"])
+    labels, info, bbox, size, kind, row_kind = device.cluster_and_summarise(ch.dx, ch.dy, int(eps), int(minPts), DBSCAN_VARIANT,
+                                                                           int(cut) if cut > 0 else 0)
     bbox, kind, row_kind = bbox.cpu().numpy(), kind.cpu().numpy(), row_kind.cpu().numpy()
     for b in bbox[kind == 1].tolist():
         dataI.append([key[0], b[0], b[1], key[1], b[2], b[3]])

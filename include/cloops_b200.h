@@ -87,9 +87,13 @@ CLOOPS_API void cloops_index_free(cloops_index* ix);
 CLOOPS_API int64_t cloops_index_n_active(const cloops_index* ix);
 /* one launch of the region-query kernel over the index; d_counts_sorted int32[n_active] in index order */
 CLOOPS_API int cloops_index_count(cloops_index* ix, int32_t cap, int32_t* d_counts_sorted, void* stream);
-/* labels for one minPts over a built index (v1/v2 only) */
+/* labels for one minPts over a built index (v1/v2 only).  d_labels: row order (as cloops_dbscan);
+ * d_labels_sorted (may be NULL): int32[n_active], the same labels in index order. */
 CLOOPS_API int cloops_index_dbscan(cloops_index* ix, int32_t minPts, int32_t variant, int32_t* d_labels,
-                        int64_t* h_info, void* stream);
+                        int32_t* d_labels_sorted, int64_t* h_info, void* stream);
+/* X, Y of the active PETs in index order (int32[n_active] each), decoded from the packed keys.  Index
+ * order is spatially coherent, which makes cloops_cluster_summary over (xs, ys, labels_sorted) cheap. */
+CLOOPS_API int cloops_index_coords(cloops_index* ix, int32_t* d_xs, int32_t* d_ys, void* stream);
 
 /* ---- cluster -> candidate records (pipe.py:76-109) ---------------------------------------------
  * n_clusters = max id + 1.  d_bbox int32[n_clusters,4] = minX,maxX,minY,maxY ; d_size int32[n_clusters]
@@ -99,6 +103,10 @@ CLOOPS_API int cloops_index_dbscan(cloops_index* ix, int32_t minPts, int32_t var
 CLOOPS_API int cloops_cluster_summary(const int32_t* d_x, const int32_t* d_y, const int32_t* d_labels, int64_t n,
                            int64_t n_clusters, int32_t* d_bbox, int32_t* d_size, uint8_t* d_kind,
                            uint8_t* d_row_kind, void* stream);
+
+/* d_row_kind[i] = d_kind[d_labels[i]] (0 for unlabelled rows): membership of dis / dss (pipe.py:106-109) */
+CLOOPS_API int cloops_row_kinds(const int32_t* d_labels, int64_t n, const uint8_t* d_kind, int64_t n_clusters,
+                     uint8_t* d_row_kind, void* stream);
 
 /* ---- permuted-local-background range counts (cModel.py:60-143) ---------------------------------
  * A coverage model is the chromosome's PETs sorted once by X and once by Y (the reference's
