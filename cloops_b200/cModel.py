@@ -169,11 +169,26 @@ def removeDup(ds, bpcut=1e-5):
     taken = np.zeros(n, dtype=bool)
     uniqueds = {}
     groups = {}
+    # Two loops can only overlap if their left anchors intersect, i.e. a0_j lies in [a0_i - wmax, a1_i]
+    # (wmax = widest left anchor).  Looking candidates up in an a0-sorted index keeps the reference's
+    # greedy, order-dependent grouping (leader = first key, members in key order) at O(n log n).
+    proper = bool(np.all(a0 <= a1) and np.all(b0 <= b1))
+    if proper:
+        order = np.argsort(a0, kind="stable")
+        a0s = a0[order]
+        wmax = int((a1 - a0).max())
     for i in range(n - 1):
         if taken[i]:
             continue
-        j = np.arange(i + 1, n)
-        j = j[~taken[i + 1:]]
+        if proper:
+            lo = np.searchsorted(a0s, a0[i] - wmax, side="left")
+            hi = np.searchsorted(a0s, a1[i], side="right")
+            j = order[lo:hi]
+            j = np.sort(j[(j > i)])
+            j = j[~taken[j]]
+        else:
+            j = np.arange(i + 1, n)
+            j = j[~taken[i + 1:]]
         if len(j):
             hit = (chrom[j] == chrom[i]) & _end_overlap(a0[i], a1[i], a0[j], a1[j]) & _end_overlap(b0[i], b1[i], b0[j], b1[j])
             j = j[hit]

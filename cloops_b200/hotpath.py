@@ -37,24 +37,37 @@ def run_device(dx: torch.Tensor, dy: torch.Tensor, eps: int, minPts: int, varian
 
 class HostStep:
     """The same pass from HOST buffers: pinned int32 X, Y in; candidate records, per-PET kind bytes and
-    range counts out.  Staging buffers are allocated once and re-used."""
+    range counts out.  Device staging buffers and pinned result buffers are allocated once and re-used;
+    all copies are asynchronous on the current stream with one synchronisation at the end."""
 
     def __init__(self, n: int, device_index: int | None = None):
         dev = torch.device("cuda", torch.cuda.current_device() if device_index is None else device_index)
         self.dx = torch.empty(n, dtype=torch.int32, device=dev)
         self.dy = torch.empty(n, dtype=torch.int32, device=dev)
         self.h_row_kind = torch.empty(n, dtype=torch.uint8).pin_memory()
+        self._pinned = {}
         self.h2d_bytes = 2 * 4 * n
         self.d2h_bytes = 0
+
+    def _out(self, name: str, t: torch.Tensor) -> torch.Tensor:
+        """Pinned host buffer (grown geometrically) receiving an async copy of device tensor t."""
+        need = t.numel()
+        buf = self._pinned.get(name)
+        if buf is None or buf.numel() < need or buf.dtype != t.dtype:
+            buf = torch.empty(max(need * 2, 1024), dtype=t.dtype).pin_memory()
+            self._pinned[name] = buf
+        view = buf[:need].view(t.shape)
+        view.copy_(t, non_blocking=True)
+        return view
 
     def __call__(self, hx: torch.Tensor, hy: torch.Tensor, eps: int, minPts: int, variant: int = _lib.V2):
         self.dx.copy_(hx, non_blocking=True)
         self.dy.copy_(hy, non_blocking=True)
         r = run_device(self.dx, self.dy, eps, minPts, variant)
         self.h_row_kind.copy_(r.row_kind, non_blocking=True)
-        bbox = r.bbox.cpu()
-        kind = r.kind.cpu()
-        counts = r.counts.cpu()
+        bbox = self._out("bbox", r.bbox)
+        kind = self._out("kind", r.kind)
+        counts = self._out("counts", r.counts)
         torch.cuda.current_stream().synchronize()
         self.d2h_bytes = self.h_row_kind.numel() + bbox.numel() * 4 + kind.numel() + counts.numel() * 4
         return bbox, kind, counts, self.h_row_kind

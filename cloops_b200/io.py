@@ -62,55 +62,140 @@ def _cis_pets(fs, cs, cut, logger, need_strand):
     _cis_pets.total = i
 
 
-def _write_jd(fout, per_chrom, order):
+def _write_jd(fout, chrom_arrays, order):
     cfs = []
     for c in order:
-        rows = per_chrom[c]
-        mat = np.empty((len(rows) // 2, 3), dtype=np.int64)
-        mat[:, 0] = np.arange(mat.shape[0])
-        mat[:, 1] = rows[0::2]
-        mat[:, 2] = rows[1::2]
+        a, b = chrom_arrays[c]
+        mat = np.empty((len(a), 3), dtype=np.int64)
+        mat[:, 0] = np.arange(len(a))
+        mat[:, 1] = a
+        mat[:, 2] = b
         f = os.path.join(fout, "%s-%s.jd" % (c, c))
         joblib.dump(mat, f)
         cfs.append(f)
     return cfs
 
 
+_INT_RE = r"^[+-]?[0-9]+$"
+
+
+def _cis_table(f, cs, cut):
+    """Columnar ingest of one BEDPE file: the C tokenizer of pandas splits the lines, numpy does the PET
+    arithmetic (cLoops/io.py:47-58).  Lines the reference would have to think about (non-plain integers,
+    fewer than 10 fields) are re-parsed one by one through the PET class so that the accept/reject
+    decision is exactly the reference's; everything is returned in file order.
+    -> (chrom [object], cA [int64], cB [int64], opposite_strand [bool], n_lines)"""
+    import pandas as pd
+    width = 24
+    try:
+        tab = pd.read_csv(f, sep="\t", header=None, names=list(range(width)), dtype=str, quoting=3, na_filter=False,
+                          keep_default_na=False, engine="c", skip_blank_lines=False, compression="infer")
+    except Exception:
+        tab = None
+    if tab is None or len(tab) == 0:
+        rows = list(_cis_pets([f], cs, cut, _NullLog(), True))
+        return (np.array([r[0] for r in rows], dtype=object), np.array([r[1] for r in rows], dtype=np.int64),
+                np.array([r[2] for r in rows], dtype=np.int64), np.array([r[3] for r in rows], dtype=bool), getattr(_cis_pets, "total", 0))
+    n = len(tab)
+    cols = [tab[k] for k in range(width)]
+    filled = np.column_stack([c.to_numpy(dtype=object) != "" for c in cols])          # trailing pads are ""
+    nfields = np.where(filled.any(axis=1), width - np.argmax(filled[:, ::-1], axis=1), 1)
+    vals = np.column_stack([c.to_numpy(dtype=object) for c in cols])
+    star = ((vals == "*") & filled).any(axis=1) & (vals == "-1").any(axis=1)           # io.py:159
+    plain = np.ones(n, dtype=bool)
+    for k in (1, 2, 4, 5):
+        plain &= cols[k].str.match(_INT_RE).to_numpy()
+    # an overlong line or a line ending in empty fields is left to the slow path
+    fast = plain & (nfields >= 10) & (nfields < width) & ~star
+    slow = ~fast & ~star & (nfields >= 6)
+    cA = np.zeros(n, dtype=np.int64)
+    cB = np.zeros(n, dtype=np.int64)
+    keep = np.zeros(n, dtype=bool)
+    opp = np.zeros(n, dtype=bool)
+    chrom = cols[0].to_numpy(dtype=object)
+    if fast.any():
+        idx = np.flatnonzero(fast)
+        sA = cols[1].to_numpy(dtype=object)[idx].astype(np.int64)
+        eA = cols[2].to_numpy(dtype=object)[idx].astype(np.int64)
+        sB = cols[4].to_numpy(dtype=object)[idx].astype(np.int64)
+        eB = cols[5].to_numpy(dtype=object)[idx].astype(np.int64)
+        cis = chrom[idx] == cols[3].to_numpy(dtype=object)[idx]
+        swap = (sA + eA) > (sB + eB)                                                   # io.py:51-54
+        a = np.where(swap, (sB + eB) // 2, (sA + eA) // 2)
+        b = np.where(swap, (sA + eA) // 2, (sB + eB) // 2)
+        ok = cis.copy()
+        if len(cs) > 0:
+            ok &= np.isin(chrom[idx], list(cs))
+        if cut > 0:
+            ok &= (b - a) >= cut
+        cA[idx], cB[idx], keep[idx] = a, b, ok
+        opp[idx] = cols[8].to_numpy(dtype=object)[idx] != cols[9].to_numpy(dtype=object)[idx]
+    for k in np.flatnonzero(slow).tolist():
+        t = [v for v in vals[k, :nfields[k]]]
+        try:
+            pet = PET(t)
+        except Exception:
+            continue
+        if pet.chromA != pet.chromB or (len(cs) > 0 and pet.chromA not in cs) or (cut > 0 and pet.distance < cut):
+            continue
+        cA[k], cB[k], keep[k], opp[k] = pet.cA, pet.cB, True, pet.strandA != pet.strandB
+    return chrom[keep], cA[keep], cB[keep], opp[keep], n
+
+
+class _NullLog:
+    def info(self, *a, **k):
+        pass
+
+
+def _group_by_chrom(chrom, a, b):
+    """file order inside each chromosome, chromosomes in order of first appearance"""
+    import pandas as pd
+    codes, uniques = pd.factorize(chrom, sort=False)
+    out, order = {}, []
+    for k, name in enumerate(uniques.tolist()):
+        m = codes == k
+        out[name] = (a[m], b[m])
+        order.append(name)
+    return out, order
+
+
 def parseRawBedpe2(fs, fout, cs, cut, logger):
     """cLoops/io.py:132-189 + txt2jd (:192-203) in one step: per-chromosome ``[id, cA, cB]`` int64
     matrices (id restarts at 0 per chromosome, rows in file order) written straight to ``.jd``.
     Returns the list of .jd paths in order of first appearance."""
-    per, order, j = {}, [], 0
-    for c, a, b, _ in _cis_pets(fs, cs, cut, logger, False):
-        if c not in per:
-            per[c] = []
-            order.append(c)
-        per[c].append(a)
-        per[c].append(b)
-        j += 1
-    logger.info("Totaly %s PETs from %s, in which %s cis PETs" % (getattr(_cis_pets, "total", 0), ",".join(fs), j))
+    parts, total = [], 0
+    for f in fs:
+        logger.info("Parsing PETs from %s, requiring initial distance cutoff > %s" % (f, cut))
+        chrom, a, b, _, n = _cis_table(f, cs, cut)
+        parts.append((chrom, a, b))
+        total += n
+    chrom = np.concatenate([p[0] for p in parts]) if parts else np.zeros(0, dtype=object)
+    a = np.concatenate([p[1] for p in parts]) if parts else np.zeros(0, np.int64)
+    b = np.concatenate([p[2] for p in parts]) if parts else np.zeros(0, np.int64)
+    logger.info("Totaly %s PETs from %s, in which %s cis PETs" % (total, ",".join(fs), len(a)))
+    per, order = _group_by_chrom(chrom, a, b)
     return _write_jd(fout, per, order)
 
 
 def parseRawBedpe(fs, fout, cs, cut, logger):
-    """cLoops/io.py:62-129: as parseRawBedpe2 but drops duplicate (cA, cB) per chromosome and collects
-    the distances of opposite-strand PETs (input of estFragSize when eps is auto-estimated)."""
-    per, order, seen, ds, j = {}, [], {}, [], 0
-    for c, a, b, opp in _cis_pets(fs, cs, cut, logger, True):
-        if c not in per:
-            per[c] = []
-            seen[c] = set()
-            order.append(c)
-        if (a, b) in seen[c]:
-            continue
-        seen[c].add((a, b))
-        per[c].append(a)
-        per[c].append(b)
-        j += 1
-        if opp:
-            ds.append(b - a)
-    logger.info("Totaly %s PETs from %s, in which %s cis PETs" % (getattr(_cis_pets, "total", 0), ",".join(fs), j))
-    return _write_jd(fout, per, order), ds
+    """cLoops/io.py:62-129: as parseRawBedpe2 but drops duplicate (cA, cB) per chromosome (first one
+    wins) and collects the distances of opposite-strand PETs (input of estFragSize when eps is auto)."""
+    import pandas as pd
+    parts, total = [], 0
+    for f in fs:
+        logger.info("Parsing PETs from %s, requiring initial distance cutoff > %s" % (f, cut))
+        chrom, a, b, opp, n = _cis_table(f, cs, cut)
+        parts.append((chrom, a, b, opp))
+        total += n
+    chrom = np.concatenate([p[0] for p in parts]) if parts else np.zeros(0, dtype=object)
+    a = np.concatenate([p[1] for p in parts]) if parts else np.zeros(0, np.int64)
+    b = np.concatenate([p[2] for p in parts]) if parts else np.zeros(0, np.int64)
+    opp = np.concatenate([p[3] for p in parts]) if parts else np.zeros(0, bool)
+    first = ~pd.DataFrame({"c": chrom, "a": a, "b": b}).duplicated(keep="first").to_numpy() if len(a) else np.zeros(0, bool)
+    chrom, a, b, opp = chrom[first], a[first], b[first], opp[first]
+    logger.info("Totaly %s PETs from %s, in which %s cis PETs" % (total, ",".join(fs), len(a)))
+    per, order = _group_by_chrom(chrom, a, b)
+    return _write_jd(fout, per, order), (b - a)[opp].tolist()
 
 
 def txt2jd(f):

@@ -158,3 +158,34 @@ def test_two_rank_gloo(tmp_path):
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert (tmp_path / "ok").exists()
+
+
+def test_columnar_ingest_equals_line_parser(tmp_path):
+    """The pandas/numpy ingest must accept, orient and order PETs exactly like the per-line PET class
+    (cLoops/io.py:30-59,150-183), including on malformed lines."""
+    rng = np.random.default_rng(4)
+    lines = []
+    for k in range(4000):
+        c1 = "chr%d" % rng.integers(1, 4)
+        c2 = c1 if rng.random() < 0.8 else "chr%d" % rng.integers(1, 4)
+        a = int(rng.integers(0, 100000)); b = int(rng.integers(0, 100000))
+        t = [c1, str(a), str(a + int(rng.integers(0, 200))), c2, str(b), str(b + int(rng.integers(0, 200))), "n%d" % k, ".",
+             "+-"[rng.integers(0, 2)], "+-"[rng.integers(0, 2)]]
+        r = rng.random()
+        if r < 0.02: t = t[:int(rng.integers(1, 10))]            # short line
+        elif r < 0.04: t[1] = "x12"                               # not an int
+        elif r < 0.06: t[4] = " 77"                               # int() accepts, the regex does not: slow path
+        elif r < 0.08: t[2] = "+5"                                # signed
+        elif r < 0.10: t = ["*", "-1", "-1", "*", "-1", "-1", "n", ".", "+", "-"]
+        elif r < 0.12: t += ["extra", "cols"]
+        elif r < 0.13: t = [""]
+        elif r < 0.14: t[5] = "1_0"                               # python int() accepts underscores
+        lines.append("\t".join(t))
+    f = tmp_path / "w.bedpe"
+    f.write_text("\n".join(lines) + "\n")
+    for cs, cut in (([], 0), ({"chr1", "chr3"}, 0), ([], 5000)):
+        want = list(io._cis_pets([str(f)], cs, cut, logging.getLogger("t"), True))
+        chrom, a, b, opp, n = io._cis_table(str(f), cs, cut)
+        got = list(zip(chrom.tolist(), a.tolist(), b.tolist(), opp.tolist()))
+        assert got == want
+        assert n == len(lines)
