@@ -32,6 +32,16 @@ EPS, MINPTS = 1000, 5
 CHROM_LEN = 249_000_000
 
 
+def load_traffic(n_pets):
+    """DRAM bytes per launch of the region-query kernel from the committed ncu capture (same workload)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_count_kernel_metrics.json")) as fh:
+            m = json.load(fh)
+        return float(m["traffic_bytes"]) if int(m["n_pets"]) == int(n_pets) else None
+    except Exception:
+        return None
+
+
 def load_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -277,7 +287,7 @@ def main():
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "count_kernel (region query)", "achieved": achieved, "peak": peak,
                      "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback 6650 GB/s",
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "ms": t_rq,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": load_traffic(n_act), "ms": t_rq,
                      "algorithmic_bytes": 12 * n_act, "frac_of_8TBs_nominal": achieved / 8000.0},
         "stages_ms": stage_avg,
         "result": {"clusters": r.info["n_clusters"], "core": r.info["n_core"], "dead": r.info["n_dead"],

@@ -75,3 +75,30 @@ def test_sample_window_matches_oracle(big):
         got, _ = device.dbscan_device(device.to_device_i32(xs), device.to_device_i32(ys), EPS, MP, variant)
         want = fn(xs.astype(np.int64), ys.astype(np.int64), EPS, MP)
         assert np.array_equal(got.cpu().numpy(), want), variant
+
+
+def test_index_reuse_sweep_matches_fresh_runs():
+    """BASELINE.json configs[4] (eps x minPts sweep): one resident index per eps serves every minPts
+    and both strip-index variants; results must equal independent runs."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from cloops_b200 import device, synth
+    X, Y = synth.config2(2_000_000, seed=77)
+    dx, dy = device.to_device_i32(X), device.to_device_i32(Y)
+    for eps in (500, 2500, 10000):
+        ix = device.Index(dx, dy, eps)
+        try:
+            for mp in (50, 5, 20):
+                for variant in (2, 1):
+                    lab, ls, info = ix.dbscan(mp, variant, want_sorted=True)
+                    ref, rinfo = device.dbscan_device(dx, dy, eps, mp, variant)
+                    assert torch.equal(lab, ref), (eps, mp, variant)
+                    assert info == rinfo
+                    xs, ys = ix.coords()
+                    # index order is a permutation of the rows: same multiset of (x, y, label)
+                    a = torch.stack([xs.long(), ys.long(), ls.long()], 1)
+                    b = torch.stack([dx.long(), dy.long(), lab.long()], 1)
+                    key = lambda t: (t[:, 0] * 1_000_003 + t[:, 1] * 7 + t[:, 2]).sort().values
+                    assert torch.equal(key(a), key(b))
+        finally:
+            ix.close()
