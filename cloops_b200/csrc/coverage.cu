@@ -74,41 +74,48 @@ __device__ __forceinline__ int upper_bound_i(const int* __restrict__ a, int n, i
     return lo;
 }
 
-// one CTA per candidate.  out row: ra, rb, rab, na[10], nb[10], C[10][10]
+// One WARP per candidate (4 candidates per CTA), no CTA-wide barriers: lane 0 derives the windows, up to
+// 8 lanes run the slice binary searches, then the 32 lanes stride over the X-sorted and Y-sorted slices.
+// out row: ra, rb, rab, na[10], nb[10], C[10][10]
+#define RC_WARPS 4
 template <int WIN>
-__global__ void __launch_bounds__(128) range_count_kernel(const int* __restrict__ xs_x, const int* __restrict__ xs_y,
-                                                          const int* __restrict__ ys_y, const int* __restrict__ ys_x, int n,
-                                                          const int* __restrict__ cand, int* __restrict__ out) {
+__global__ void __launch_bounds__(32 * RC_WARPS) range_count_kernel(const int* __restrict__ xs_x, const int* __restrict__ xs_y,
+                                                                    const int* __restrict__ ys_y, const int* __restrict__ ys_x, int n,
+                                                                    const int* __restrict__ cand, long long ncand, int* __restrict__ out) {
     constexpr int NOUT = (WIN > 0) ? 123 : 3;
     constexpr int NWIN = (WIN > 0) ? NW : 1;
-    __shared__ Windows W;
-    __shared__ int acc[NOUT];
-    __shared__ int seg[8];   // [h][0..1] = X-sorted slice, [h][2..3] = Y-sorted slice
-    const int m = blockIdx.x;
-    const int4 c = __ldg(reinterpret_cast<const int4*>(cand) + m);
-    for (int t = threadIdx.x; t < NOUT; t += blockDim.x) acc[t] = 0;
-    if (threadIdx.x == 0) make_windows(c.x, c.y, c.z, c.w, WIN, W);
-    __syncthreads();
-    if (threadIdx.x < 4 * W.nh) {
-        int h = threadIdx.x >> 2, which = threadIdx.x & 3;
-        int r;
-        if (which == 0) r = lower_bound_i(xs_x, n, W.h0[h]);
-        else if (which == 1) r = upper_bound_i(xs_x, n, W.h1[h]);
-        else if (which == 2) r = lower_bound_i(ys_y, n, W.h0[h]);
-        else r = upper_bound_i(ys_y, n, W.h1[h]);
-        seg[threadIdx.x] = r;
+    __shared__ Windows Ws[RC_WARPS];
+    __shared__ int accs[RC_WARPS][NOUT];
+    const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long m = (long long)blockIdx.x * RC_WARPS + wl;
+    if (m >= ncand) return;                                    // whole warp
+    Windows& W = Ws[wl];
+    int* acc = accs[wl];
+    for (int t = lane; t < NOUT; t += 32) acc[t] = 0;
+    if (lane == 0) {
+        const int4 c = __ldg(reinterpret_cast<const int4*>(cand) + m);
+        make_windows(c.x, c.y, c.z, c.w, WIN, W);
     }
-    __syncthreads();
+    __syncwarp();
     const int nh = W.nh;
+    int myseg = 0;
+    if (lane < 4 * nh) {
+        const int h = lane >> 2, which = lane & 3;
+        if (which == 0) myseg = lower_bound_i(xs_x, n, W.h0[h]);
+        else if (which == 1) myseg = upper_bound_i(xs_x, n, W.h1[h]);
+        else if (which == 2) myseg = lower_bound_i(ys_y, n, W.h0[h]);
+        else myseg = upper_bound_i(ys_y, n, W.h1[h]);
+    }
     for (int pass = 0; pass < 2 * nh; ++pass) {
         const int h = pass >> 1, via_y = pass & 1;
-        const int lo = seg[4 * h + 2 * via_y], hi = seg[4 * h + 2 * via_y + 1];
-        for (int t = lo + threadIdx.x; t < hi; t += blockDim.x) {
-            int x, y;
-            if (!via_y) { x = __ldg(xs_x + t); y = __ldg(xs_y + t); }
-            else {
-                y = __ldg(ys_y + t); x = __ldg(ys_x + t);
-                bool seen = false;           // already visited through its X
+        const int lo = __shfl_sync(0xffffffffu, myseg, 4 * h + 2 * via_y);
+        const int hi = __shfl_sync(0xffffffffu, myseg, 4 * h + 2 * via_y + 1);
+        const int* __restrict__ pa = via_y ? ys_x : xs_x;      // x coordinate source
+        const int* __restrict__ pb = via_y ? ys_y : xs_y;      // y coordinate source
+        for (int t = lo + lane; t < hi; t += 32) {
+            const int x = __ldg(pa + t), y = __ldg(pb + t);
+            if (via_y) {
+                bool seen = false;                             // already visited through its X
                 for (int g = 0; g < nh; ++g) seen |= (x >= W.h0[g] && x <= W.h1[g]);
                 if (seen) continue;
             }
@@ -120,15 +127,15 @@ __global__ void __launch_bounds__(128) range_count_kernel(const int* __restrict_
             if (xa || ya) {
 #pragma unroll
                 for (int w = 0; w < NWIN; ++w) {
-                    const int lo = W.a0[w], hi = W.a1[w];
-                    ma |= (((x >= lo && x <= hi) || (y >= lo && y <= hi)) ? 1u : 0u) << w;
+                    const int l = W.a0[w], u = W.a1[w];
+                    ma |= (((x >= l && x <= u) || (y >= l && y <= u)) ? 1u : 0u) << w;
                 }
             }
             if (xb || yb) {
 #pragma unroll
                 for (int w = 0; w < NWIN; ++w) {
-                    const int lo = W.b0[w], hi = W.b1[w];
-                    mb |= (((x >= lo && x <= hi) || (y >= lo && y <= hi)) ? 1u : 0u) << w;
+                    const int l = W.b0[w], u = W.b1[w];
+                    mb |= (((x >= l && x <= u) || (y >= l && y <= u)) ? 1u : 0u) << w;
                 }
             }
             if ((ma | mb) == 0) continue;
@@ -146,13 +153,8 @@ __global__ void __launch_bounds__(128) range_count_kernel(const int* __restrict_
             }
         }
     }
-    __syncthreads();
-    for (int t = threadIdx.x; t < NOUT; t += blockDim.x) out[(long long)m * NOUT + t] = acc[t];
-}
-
-__global__ void __launch_bounds__(256) iota_kernel(int* p, int n) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = i;
+    __syncwarp();
+    for (int t = lane; t < NOUT; t += 32) out[m * NOUT + t] = acc[t];
 }
 
 }  // namespace cloops
@@ -213,7 +215,7 @@ int cloops_range_counts(const cloops_coverage* cov, const int32_t* d_cand, int64
     stages_begin(st);
     if (m > 0) {
         if (cov->n == 0) CU_TRY(cudaMemsetAsync(d_out, 0, (size_t)m * 123 * sizeof(int), st));
-        else LAUNCH(range_count_kernel<5>, (unsigned)m, 128, 0, st, cov->xs_x, cov->xs_y, cov->ys_y, cov->ys_x, cov->n, d_cand, d_out);
+        else LAUNCH(range_count_kernel<5>, (unsigned)((m + RC_WARPS - 1) / RC_WARPS), 32 * RC_WARPS, 0, st, cov->xs_x, cov->xs_y, cov->ys_y, cov->ys_x, cov->n, d_cand, (long long)m, d_out);
     }
     stage_mark("range_counts", st);
     return stages_end(st);
@@ -226,7 +228,7 @@ int cloops_region_pets(const cloops_coverage* cov, const int32_t* d_cand, int64_
     stages_begin(st);
     if (m > 0) {
         if (cov->n == 0) CU_TRY(cudaMemsetAsync(d_out, 0, (size_t)m * 3 * sizeof(int), st));
-        else LAUNCH(range_count_kernel<0>, (unsigned)m, 128, 0, st, cov->xs_x, cov->xs_y, cov->ys_y, cov->ys_x, cov->n, d_cand, d_out);
+        else LAUNCH(range_count_kernel<0>, (unsigned)((m + RC_WARPS - 1) / RC_WARPS), 32 * RC_WARPS, 0, st, cov->xs_x, cov->xs_y, cov->ys_y, cov->ys_x, cov->n, d_cand, (long long)m, d_out);
     }
     stage_mark("region_pets", st);
     return stages_end(st);
