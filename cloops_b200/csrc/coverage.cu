@@ -31,7 +31,21 @@ struct Windows {
     int h0[2], h1[2];    // disjoint hull intervals (merged when the two families overlap)
     int nh;
     int fa0, fa1, fb0, fb1;   // hull of the A family / of the B family (anchor included)
+    int2 A[NW], B[NW];        // (lo, hi - lo) per window for the one-subtract range test; empty windows -> (INT_MAX, 0)
 };
+
+// c in [lo, lo + width]  <=>  (unsigned)(c - lo) <= width   (coordinates are < 2^30 in magnitude, no wrap)
+__device__ __forceinline__ unsigned window_mask(const int2* __restrict__ win, int nwin, int c) {
+    unsigned m = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        if (w < nwin) {
+            const int2 t = win[w];
+            m |= (((unsigned)(c - t.x) <= (unsigned)t.y) ? 1u : 0u) << w;
+        }
+    }
+    return m;
+}
 
 __device__ __forceinline__ long long fdiv2(long long a) { return (a >= 0) ? a / 2 : -((-a + 1) / 2); }  // floor(a/2)
 
@@ -58,6 +72,10 @@ __device__ void make_windows(int iva0, int iva1, int ivb0, int ivb1, int win, Wi
         hb0 = min(hb0, W.b0[w]); hb1 = max(hb1, W.b1[w]);
     }
     W.fa0 = ha0; W.fa1 = ha1; W.fb0 = hb0; W.fb1 = hb1;
+    for (int w = 0; w < NW; ++w) {
+        W.A[w] = (w < nw && W.a0[w] <= W.a1[w]) ? make_int2(W.a0[w], W.a1[w] - W.a0[w]) : make_int2(INT_MAX, 0);
+        W.B[w] = (w < nw && W.b0[w] <= W.b1[w]) ? make_int2(W.b0[w], W.b1[w] - W.b0[w]) : make_int2(INT_MAX, 0);
+    }
     if (ha0 > hb0) { int t = ha0; ha0 = hb0; hb0 = t; t = ha1; ha1 = hb1; hb1 = t; }
     if (hb0 <= ha1) { W.nh = 1; W.h0[0] = ha0; W.h1[0] = max(ha1, hb1); }
     else { W.nh = 2; W.h0[0] = ha0; W.h1[0] = ha1; W.h0[1] = hb0; W.h1[1] = hb1; }
@@ -112,8 +130,12 @@ __global__ void __launch_bounds__(32 * RC_WARPS) range_count_kernel(const int* _
         const int hi = __shfl_sync(0xffffffffu, myseg, 4 * h + 2 * via_y + 1);
         const int* __restrict__ pa = via_y ? ys_x : xs_x;      // x coordinate source
         const int* __restrict__ pb = via_y ? ys_y : xs_y;      // y coordinate source
-        for (int t = lo + lane; t < hi; t += 32) {
-            const int x = __ldg(pa + t), y = __ldg(pb + t);
+        int t = lo + lane;
+        int xn = 0, yn = 0;
+        if (t < hi) { xn = __ldg(pa + t); yn = __ldg(pb + t); }
+        for (; t < hi; t += 32) {
+            const int x = xn, y = yn;
+            if (t + 32 < hi) { xn = __ldg(pa + t + 32); yn = __ldg(pb + t + 32); }   // prefetch the next PET
             if (via_y) {
                 bool seen = false;                             // already visited through its X
                 for (int g = 0; g < nh; ++g) seen |= (x >= W.h0[g] && x <= W.h1[g]);
@@ -124,20 +146,10 @@ __global__ void __launch_bounds__(32 * RC_WARPS) range_count_kernel(const int* _
             unsigned ma = 0, mb = 0;
             const bool xa = x >= W.fa0 && x <= W.fa1, ya = y >= W.fa0 && y <= W.fa1;
             const bool xb = x >= W.fb0 && x <= W.fb1, yb = y >= W.fb0 && y <= W.fb1;
-            if (xa || ya) {
-#pragma unroll
-                for (int w = 0; w < NWIN; ++w) {
-                    const int l = W.a0[w], u = W.a1[w];
-                    ma |= (((x >= l && x <= u) || (y >= l && y <= u)) ? 1u : 0u) << w;
-                }
-            }
-            if (xb || yb) {
-#pragma unroll
-                for (int w = 0; w < NWIN; ++w) {
-                    const int l = W.b0[w], u = W.b1[w];
-                    mb |= (((x >= l && x <= u) || (y >= l && y <= u)) ? 1u : 0u) << w;
-                }
-            }
+            if (xa) ma |= window_mask(W.A, NWIN, x);
+            if (ya) ma |= window_mask(W.A, NWIN, y);
+            if (xb) mb |= window_mask(W.B, NWIN, x);
+            if (yb) mb |= window_mask(W.B, NWIN, y);
             if ((ma | mb) == 0) continue;
             if (ma & 1u) atomicAdd(&acc[0], 1);
             if (mb & 1u) atomicAdd(&acc[1], 1);
