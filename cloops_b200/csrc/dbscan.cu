@@ -14,6 +14,7 @@
 #include <limits.h>
 
 #include <cub/cub.cuh>
+#include <thrust/iterator/reverse_iterator.h>
 
 #include "index.cuh"
 
@@ -117,30 +118,43 @@ __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
 //    gaps are <= eps).  A chain is one connected set, so it needs no union-find at all: a core point
 //    is a chain head iff it has no core point within eps on its left, and every core point's parent is
 //    the latest head at or before it -- one inclusive max-scan over the head indices.
-//  * strip s-1: inside the u-window at most two chains of strip s-1 are visible; one union per visible
-//    chain (through any member that passes the v test) is enough.  Only these cross-strip links go
-//    through the lock-free union-find, whose trees start out flat (depth 1).
+//  * strip s-1: one union per chain of strip s-1 that has a member inside the window passing the v test
+//    is enough; after linking, the scan jumps to the next chain head (suffix-min scan of head indices),
+//    so a core point costs O(#chains in its window), not O(#points) -- dense Hi-C strips hold hundreds
+//    of chain members per window.  Only these cross-strip links go through the lock-free union-find,
+//    whose trees start out flat (depth 1).
 __global__ void __launch_bounds__(256) chain_head_kernel(const u64* __restrict__ keys, const int* __restrict__ sstart, GridParams P,
-                                                         int* __restrict__ head) {
+                                                         int* __restrict__ head, int* __restrict__ head_or_inf) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n_act) return;
     const u64 key = keys[i];
-    int h = 0;
+    int h = i;
     if (key >> 63) {
         const PointView p = view(key, P);
         const int lo_s = __ldg(sstart + p.s + 1);
-        h = i;
         for (int j = i - 1; j >= lo_s; --j) {
             u64 kq = keys[j];
             if (((u32)(kq >> P.be) & P.umask) < p.ulo) break;
-            if (kq >> 63) { h = 0; break; }
+            if (kq >> 63) { h = -1; break; }
         }
+    } else {
+        h = -1;
     }
-    head[i] = h;
+    head[i] = h < 0 ? 0 : h;
+    head_or_inf[i] = h < 0 ? INT_MAX : h;      // input of the suffix-min that yields "next chain head after i"
 }
 
+__global__ void __launch_bounds__(256) clamp_next_head_kernel(int* __restrict__ nh, int na) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < na && nh[i] > na) nh[i] = na;
+}
+
+// chain[] = immutable chain head per core point (the scan output); seen[hA] remembers the last chain of
+// strip s-1 that chain hA was linked to, so the many members of hA that look at the same chain below
+// skip the union (and its pointer chasing) after one cached load.
 __global__ void __launch_bounds__(256) union_kernel(const u64* __restrict__ keys, const int* __restrict__ sstart, GridParams P,
-                                                    int* __restrict__ parent) {
+                                                    const int* __restrict__ chain, const int* __restrict__ next_head,
+                                                    int* __restrict__ seen, int* __restrict__ parent) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n_act) return;
     const u64 key = keys[i];
@@ -149,19 +163,24 @@ __global__ void __launch_bounds__(256) union_kernel(const u64* __restrict__ keys
     const int lo_s = __ldg(sstart + p.s + 1);
     const int a = __ldg(sstart + p.s);
     if (a < lo_s) {
+        const int ha = chain[i];
         u64 base = (u64)(p.s - 1) << P.bu;
         int j = lower_bound_su(keys, a, lo_s, base | p.ulo, P.be);
         u64 top = base | p.uhi;
-        long long last_core_u = -(1LL << 40);
-        bool linked = false;
         for (; j < lo_s; ++j) {
             u64 kq = keys[j];
             if (key_su(kq, P.be) > top) break;
             if (!(kq >> 63)) continue;
-            long long uq = (long long)((u32)(kq >> P.be) & P.umask);
-            if (uq - last_core_u > (long long)P.eps) linked = false;   // a new chain of strip s-1 starts
-            last_core_u = uq;
-            if (!linked && ((u32)kq & P.emask) >= p.vm) { uf_union(parent, i, j); linked = true; }
+            if (((u32)kq & P.emask) >= p.vm) {
+                const int hb = chain[j];
+                if (seen[ha] != hb) {                                  // racy hint: a stale value only costs a redundant union
+                    seen[ha] = hb;
+                    uf_union(parent, ha, hb);
+                }
+                // the rest of this chain adds nothing: continue at the next chain head (dense strips
+                // hold hundreds of chain members inside one window)
+                j = next_head[j] - 1;
+            }
         }
     }
 }
@@ -401,14 +420,35 @@ int index_dbscan(cloops_index* ix, int minPts, int variant, int* d_labels, int* 
     {
         // chains inside strips by scan (parent = latest chain head), cross-strip links by union-find
         int* head = W.assigned;                    // scratch: assigned[] is written later by compress_kernel
-        LAUNCH(chain_head_kernel, g, 256, 0, st, ix->keys, ix->sstart, P, head);
+        int* chain = W.size;                       // scratch until size_kernel / v2 survival re-initialise it
+        int* seen = W.ub;
+        int* nh_in = W.ncore;                      // scratch: ncore[] is zeroed again below
+        int* next_head;                            // next_head[i] = first chain head with index > i (or n_act)
+        RET_IF(tmp.alloc(&next_head, (size_t)na + 1));
+        LAUNCH(chain_head_kernel, g, 256, 0, st, ix->keys, ix->sstart, P, head, nh_in);
         size_t scan_bytes = 0;
-        CU_TRY(cub::DeviceScan::InclusiveScan(nullptr, scan_bytes, head, W.parent, cub::Max(), na, st));
+        CU_TRY(cub::DeviceScan::InclusiveScan(nullptr, scan_bytes, head, chain, cub::Max(), na, st));
         void* d_scan;
         RET_IF(tmp.alloc((char**)&d_scan, scan_bytes));
-        CU_TRY(cub::DeviceScan::InclusiveScan(d_scan, scan_bytes, head, W.parent, cub::Max(), na, st));
+        CU_TRY(cub::DeviceScan::InclusiveScan(d_scan, scan_bytes, head, chain, cub::Max(), na, st));
+        CU_TRY(cudaMemcpyAsync(W.parent, chain, (size_t)na * sizeof(int), cudaMemcpyDeviceToDevice, st));
+        {
+            // suffix-min over (head ? index : INT_MAX), shifted by one: scan the reversed range
+            LAUNCH(fill_int_kernel, 1, 32, 0, st, next_head + na, na, 1LL);
+            auto rin = thrust::make_reverse_iterator(nh_in + na);
+            auto rout = thrust::make_reverse_iterator(next_head + na);
+            size_t b2 = 0;
+            CU_TRY(cub::DeviceScan::InclusiveScan(nullptr, b2, rin, rout, cub::Min(), na, st));
+            void* d_s2;
+            RET_IF(tmp.alloc((char**)&d_s2, b2));
+            CU_TRY(cub::DeviceScan::InclusiveScan(d_s2, b2, rin, rout, cub::Min(), na, st));
+            LAUNCH(clamp_next_head_kernel, g, 256, 0, st, next_head, na);
+            CU_TRY(cudaMemsetAsync(W.ncore, 0, (size_t)na * sizeof(int), st));
+        }
+        CU_TRY(cudaMemsetAsync(seen, 0xff, (size_t)na * sizeof(int), st));
         stage_mark("chains", st);
-        LAUNCH(union_kernel, g, 256, 0, st, ix->keys, ix->sstart, P, W.parent);
+        LAUNCH(union_kernel, g, 256, 0, st, ix->keys, ix->sstart, P, chain, next_head + 1, seen, W.parent);
+        CU_TRY(cudaMemsetAsync(W.size, 0, (size_t)na * sizeof(int), st));
     }
     stage_mark("union", st);
     LAUNCH(compress_kernel, g, 256, 0, st, ix->keys, ix->rows, P, W, variant);

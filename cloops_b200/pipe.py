@@ -56,21 +56,23 @@ class _Resident:
         cls._cache.clear()
 
 
-def singleDBSCAN(f, eps, minPts, cut=0):
-    """cLoops/pipe.py:52-110 for one chromosome -> ``(key, f, dataI, dataS, dis, dss)``.
+def _single(f, eps, minPts, cut=0):
+    """One chromosome of one round -> (key, f, dataI, dataS, dis, dss) with dis/dss as float64 arrays.
     The cut filter, the clusterer and the per-cluster reduction all run on the GPU; the host receives
     the candidate records and one kind byte per PET."""
     ch = _Resident.get(f)
     key = ch.key
-    dataI, dataS, dis, dss = [], [], [], []
+    dataI, dataS = [], []
+    dis = np.zeros(0, np.float64)
+    dss = []
     d = ch.Y - ch.X
     if cut > 0:
-        dss.extend(d[d < cut].tolist())
+        dss.append(d[d < cut].astype(np.float64))
         n_act = int((d >= cut).sum())
     else:
         n_act = len(d)
     if n_act == 0:
-        return key, f, dataI, dataS, dis, dss
+        return key, f, dataI, dataS, dis, (np.concatenate(dss) if dss else np.zeros(0, np.float64))
     sys.stderr.write("Clustering %s and %s using eps as %s, minPts as %s,pre-set distance cutoff as > %s\n" %
                      (key[0], key[1], eps, minPts, cut))
     labels, info, bbox, size, kind, row_kind = device.cluster_and_summarise(ch.dx, ch.dy, int(eps), int(minPts), DBSCAN_VARIANT,
@@ -80,21 +82,30 @@ def singleDBSCAN(f, eps, minPts, cut=0):
         dataI.append([key[0], b[0], b[1], key[1], b[2], b[3]])
     for b in bbox[kind == 2].tolist():
         dataS.append([key[0], b[0], b[1], key[1], b[2], b[3]])
-    n_i, n_s = int((row_kind == 1).sum()), int((row_kind == 2).sum())
+    in_i, in_s = row_kind == 1, row_kind == 2
     sys.stderr.write("Clustering %s and %s finished. Estimated %s self-ligation reads and %s inter-ligation reads\n" %
-                     (key[0], key[1], n_s, n_i))
+                     (key[0], key[1], int(in_s.sum()), int(in_i.sum())))
     if len(dataI) > 0:
-        dis = d[row_kind == 1].astype(np.float64).tolist()
+        dis = d[in_i].astype(np.float64)
     if len(dataS) > 0:
-        dss.extend(d[row_kind == 2].astype(np.float64).tolist())
-    return key, f, dataI, dataS, dis, dss
+        dss.append(d[in_s].astype(np.float64))
+    return key, f, dataI, dataS, dis, (np.concatenate(dss) if dss else np.zeros(0, np.float64))
+
+
+def singleDBSCAN(f, eps, minPts, cut=0):
+    """cLoops/pipe.py:52-110 for one chromosome -> ``(key, f, dataI, dataS, dis, dss)`` (lists, as the
+    reference returns them)."""
+    key, f, dataI, dataS, dis, dss = _single(f, eps, minPts, cut)
+    return key, f, dataI, dataS, dis.tolist(), dss.tolist()
 
 
 def runDBSCAN(fs, eps, minPts, cut=0, cpu=1):
     """cLoops/pipe.py:113-127.  Chromosomes owned by this rank are clustered here; results of all ranks
-    are merged in file order so every rank returns what the reference's parent process would."""
+    are merged in file order so every rank returns what the reference's parent process would.  The
+    distance collections come back as float64 arrays (the reference returns lists; its only consumer,
+    pipe(), wraps them in np.array, pipe.py:259)."""
     mine = dist.my_share(fs)
-    part = {f: singleDBSCAN(f, eps, minPts, cut) for f in mine}
+    part = {f: _single(f, eps, minPts, cut) for f in mine}
     ds = dist.merge_in_order(fs, part)
     dataI, dataS, dis, dss = {}, [], [], []
     for d in ds:
@@ -102,8 +113,10 @@ def runDBSCAN(fs, eps, minPts, cut=0, cpu=1):
             continue
         dataI[d[0]] = {"f": d[1], "records": d[2]}
         dataS.extend(d[3])
-        dis.extend(d[4])
-        dss.extend(d[5])
+        dis.append(d[4])
+        dss.append(d[5])
+    dis = np.concatenate(dis) if dis else np.zeros(0, np.float64)
+    dss = np.concatenate(dss) if dss else np.zeros(0, np.float64)
     return dataI, dataS, dis, dss
 
 

@@ -5,6 +5,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
+import numpy as np  # noqa: E402
 import pandas as pd  # noqa: E402
 
 from cloops_b200 import dist, pipe  # noqa: E402
@@ -22,16 +23,16 @@ def fake_single(f, eps, minPts, cut=0):
     c = f.split("-")[0]
     k = weights[f]
     recs = [[c, 10 * i, 10 * i + 5, c, 1000 + 10 * i, 1000 + 10 * i + 5] for i in range(k // 10)]
-    return (c, c), f, recs if c != "chrE" else [], [[c, 1, 2, c, 3, 4]], [float(k)] * 3, [float(k + 1)] * 2
+    return (c, c), f, recs if c != "chrE" else [], [[c, 1, 2, c, 3, 4]], np.array([float(k)] * 3), np.array([float(k + 1)] * 2)
 
 
 orig_assign = dist.assign
 dist.assign = lambda items, w=None, nranks=None: orig_assign(items, [weights.get(i, 1) for i in items] if w is None else w, nranks)
-pipe.singleDBSCAN = fake_single
+pipe._single = fake_single
 dataI, dataS, dis, dss = pipe.runDBSCAN(files, 1000, 5, 0)
 # every rank sees the merged result in FILE order (pipe.py:120-127)
 assert list(dataI.keys()) == [("chrA", "chrA"), ("chrB", "chrB"), ("chrC", "chrC"), ("chrD", "chrD")], dataI.keys()
-assert dis == [50.0] * 3 + [40.0] * 3 + [30.0] * 6, dis
+assert dis.tolist() == [50.0] * 3 + [40.0] * 3 + [30.0] * 6, dis
 assert len(dataS) == 4 and len(dss) == 8
 mine = sorted(seen)
 got = dist.merge_in_order([0, 1], {dist.rank(): mine})
