@@ -189,3 +189,22 @@ def test_columnar_ingest_equals_line_parser(tmp_path):
         got = list(zip(chrom.tolist(), a.tolist(), b.tolist(), opp.tolist()))
         assert got == want
         assert n == len(lines)
+
+
+def test_facade_argument_contract():
+    """Errors that are part of the call surface and need no GPU: empty input (cDBSCAN2 -> {},
+    v1/block -> IndexError as in cDBSCAN.py:77 / blockDBSCAN.py:74), malformed mat, non-integer eps."""
+    from cloops_b200._lib import CloopsError
+    from cloops_b200.blockDBSCAN import blockDBSCAN
+    from cloops_b200.cDBSCAN import cDBSCAN as V1
+    from cloops_b200.cDBSCAN2 import cDBSCAN as V2
+    empty = np.zeros((0, 3), np.int64)
+    db = V2(empty, 1000, 5)
+    assert db.labels == {} and db.labels_array.shape == (0,)
+    for cls in (V1, blockDBSCAN):
+        with pytest.raises(IndexError):
+            cls(empty, 1000, 5)
+    with pytest.raises(CloopsError):
+        V2(np.zeros((4, 2), np.int64), 1000, 5)
+    with pytest.raises(CloopsError):
+        V2(np.zeros((4, 3), np.int64), 0.5, 5)
