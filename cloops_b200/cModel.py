@@ -112,6 +112,32 @@ def _stats(c: np.ndarray, N: int):
     return ra, rb, rab, es, fdr, hyp, pop, nbp
 
 
+def _stats_batch(counts: np.ndarray, N: int):
+    """_stats for K candidates at once -> eight arrays.  Same operations per candidate (the joint counts
+    are integers, so their sums are exact in any order; the density mean keeps numpy's row-wise pairwise
+    order); poisson/binom/hypergeom are evaluated through their array forms, which return the scalar
+    results element by element (checked against the reference's tuples in tests/test_host_logic.py)."""
+    c = np.asarray(counts)
+    K = c.shape[0]
+    ra, rb, rab = (c[:, k].astype(np.int64) for k in range(3))
+    na = c[:, 3:13].astype(np.float64)
+    nb = c[:, 13:23].astype(np.int64)
+    joint = c[:, 23:123].astype(np.float64).reshape(K, 10, 10)
+    rabs = joint.reshape(K, 100)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        dens = joint / (na[:, :, None] * nb[:, None, :])
+        nbps = np.where(joint > 0, dens, 0.0).reshape(K, 100)
+        fdr = (rabs > rab[:, None]).sum(axis=1) / 100.0
+        mrabs = np.mean(rabs, axis=1)
+        npos = (rabs > 0).sum(axis=1)
+        es = np.where(mrabs > 0, rab / (rabs.sum(axis=1) / np.maximum(npos, 1)), np.inf)
+        hyp = np.maximum(1e-300, hypergeom.sf(rab - 1.0, N, ra, rb))
+        pop = np.maximum(1e-300, poisson.sf(rab - 1.0, mrabs))
+        bp = np.mean(nbps, axis=1) * ra * rb / N
+        nbp = np.maximum(1e-300, binom.sf(rab - 1.0, N - rab, bp))
+    return ra, rb, rab, es, fdr, hyp, pop, nbp
+
+
 def getMultiplePsFdr(iva, ivb, model, N, win=5):
     """cModel.py:108-161 -> (ra, rb, rab, es, fdr, hyp, pop, nbp)."""
     if win != 5:
@@ -207,9 +233,13 @@ def removeDup(ds, bpcut=1e-5):
             ts[keys[t]] = float(d["rab"]) / d["ra"] / d["rb"]
         if not ts:
             continue
-        ts = pd.Series(ts)
-        ts.sort_values(inplace=True, ascending=False)
-        uniqueds[ts.index[0]] = ds[ts.index[0]]
+        # pandas' ``Series.sort_values(ascending=False)`` (the reference's choice of winner, :255-258),
+        # spelled out: reverse, argsort ascending with numpy's quicksort, reverse again
+        tkeys = list(ts.keys())
+        vals = np.array([ts[t] for t in tkeys], dtype=np.float64)
+        order = np.arange(len(vals))[::-1][vals[::-1].argsort(kind="quicksort")][::-1]
+        win = tkeys[int(order[0])]
+        uniqueds[win] = ds[win]
     return uniqueds
 
 
@@ -225,25 +255,19 @@ def getIntSig(f, records, minPts, discut):
     cand = np.array([[max(0, r[1]), r[2], max(0, r[4]), r[5]] for r in records], dtype=np.int64).reshape(-1, 4)
     counts = model.gpu.range_counts(cand) if len(cand) else np.zeros((0, 123), np.int32)
     need = max(minPts)
+    dist_all = np.abs((cand[:, 2] + cand[:, 3]) / 2.0 - (cand[:, 0] + cand[:, 1]) / 2.0) if len(cand) else np.zeros(0)
+    keep = np.flatnonzero((dist_all >= discut) & (counts[:, 2] >= need)) if len(cand) else np.zeros(0, np.int64)
     ds = {}
-    i = 0
-    for k, r in enumerate(records):
-        chrom = r[0]
-        key = "%s-%s-%s" % (r[0], r[3], i)
-        iva = [int(cand[k, 0]), int(cand[k, 1])]
-        ivb = [int(cand[k, 2]), int(cand[k, 3])]
-        distance = abs(sum(ivb) / 2.0 - sum(iva) / 2.0)
-        if distance < discut:
-            continue
-        if counts[k, 2] < need:
-            continue
-        i += 1
-        ra, rb, rab, es, fdr, hyp, pop, nbp = _stats(counts[k], N)
-        ds[key] = {
-            "distance": distance, "ra": ra, "rb": rb, "rab": rab, "ES": es, "FDR": fdr,
-            "hypergeometric_p-value": hyp, "poisson_p-value": pop, "binomial_p-value": nbp,
-            "iva": "%s:%s-%s" % (chrom, iva[0], iva[1]), "ivb": "%s:%s-%s" % (chrom, ivb[0], ivb[1]),
-        }
+    if len(keep):
+        ra, rb, rab, es, fdr, hyp, pop, nbp = _stats_batch(counts[keep], N)
+        for i, k in enumerate(keep.tolist()):                  # key number = accepted so far (cModel.py:280,292)
+            r = records[k]
+            chrom = r[0]
+            ds["%s-%s-%s" % (r[0], r[3], i)] = {
+                "distance": float(dist_all[k]), "ra": int(ra[i]), "rb": int(rb[i]), "rab": int(rab[i]), "ES": es[i], "FDR": fdr[i],
+                "hypergeometric_p-value": hyp[i], "poisson_p-value": pop[i], "binomial_p-value": nbp[i],
+                "iva": "%s:%s-%s" % (chrom, int(cand[k, 0]), int(cand[k, 1])), "ivb": "%s:%s-%s" % (chrom, int(cand[k, 2]), int(cand[k, 3])),
+            }
     del model
     if len(ds) == 0:
         return None

@@ -81,6 +81,25 @@ def merge_in_order(items, part: dict):
     return [merged[i] for i in items]
 
 
+def all_gather_concat(t):
+    """Concatenation over ranks (rank order) of 1-D tensors of different lengths; the result lives on
+    the device of ``t``.  Tensor collective (NCCL for CUDA tensors, gloo for CPU tensors)."""
+    if world() == 1:
+        return t
+    import torch
+    import torch.distributed as td
+    n = torch.tensor([t.numel()], dtype=torch.int64, device=t.device)
+    sizes = [torch.zeros_like(n) for _ in range(world())]
+    td.all_gather(sizes, n)
+    sizes = [int(x.item()) for x in sizes]
+    cap = max(max(sizes), 1)
+    pad = torch.zeros(cap, dtype=t.dtype, device=t.device)
+    pad[:t.numel()] = t
+    bufs = [torch.empty_like(pad) for _ in range(world())]
+    td.all_gather(bufs, pad)
+    return torch.cat([b[:k] for b, k in zip(bufs, sizes)])
+
+
 def broadcast_object(obj, src: int = 0):
     if world() == 1:
         return obj

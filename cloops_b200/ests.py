@@ -29,3 +29,44 @@ def estIntSelCutFrag(di, ds, log=1):
     rcut = int(2 ** min([cut1, cut2]))
     rfrags = int(2 ** np.median(ds))
     return rcut, rfrags
+
+
+# ---- the same estimate from per-chromosome partial statistics computed on the GPU ------------------
+# The reference pools the PET distances of all chromosomes into two Python lists and runs numpy over
+# them (cLoops/pipe.py:120-127,259).  At 10^7-10^8 PETs that host pass costs more than the whole GPU
+# round, so pipe() reduces on the device instead: per chromosome (n, mean, M2) of log2(distance) for
+# the inter- and self-ligation sets, combined with Chan's parallel formula, plus the integer self-
+# ligation distances whose order statistics give the median exactly (log2 is monotone).  Floating-point
+# summation order already differs between any two runs of the reference (its list order follows dict
+# iteration); what is reproduced, and tested against the reference's rounds, is the INTEGER cut-off.
+
+
+def combine_moments(parts):
+    """[(n, mean, M2), ...] -> (n, mean, std) with population std (numpy's default ddof=0)."""
+    n, mean, m2 = 0, 0.0, 0.0
+    for nb, mb, m2b in parts:
+        if nb == 0:
+            continue
+        if n == 0:
+            n, mean, m2 = nb, mb, m2b
+            continue
+        delta = mb - mean
+        tot = n + nb
+        m2 = m2 + m2b + delta * delta * n * nb / tot
+        mean = mean + delta * nb / tot
+        n = tot
+    std = float(np.sqrt(m2 / n)) if n else float("nan")
+    return n, mean, std
+
+
+def cut_from_moments(inter_parts, self_parts, self_sorted_distances):
+    """(rcut, rfrags) as estIntSelCutFrag; ``self_sorted_distances``: ascending positive self-ligation
+    distances (numpy or torch 1-D integer array) of all chromosomes."""
+    _, mi, si = combine_moments(inter_parts)
+    _, ms, ss = combine_moments(self_parts)
+    k = len(self_sorted_distances)
+    lo, hi = self_sorted_distances[(k - 1) // 2], self_sorted_distances[k // 2]
+    med = (float(np.log2(float(lo))) + float(np.log2(float(hi)))) / 2.0 if lo != hi else float(np.log2(float(lo)))
+    cut1 = med + 3 * ss
+    cut2 = (ms * ss + mi * si) / (ss + si)
+    return int(2 ** min([cut1, cut2])), int(2 ** med)

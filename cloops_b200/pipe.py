@@ -18,7 +18,7 @@ import pandas as pd
 
 from . import _lib, device, dist
 from .cModel import getIntSig, markIntSig, markIntSigHic
-from .ests import estFragSize, estIntSelCutFrag
+from .ests import cut_from_moments, estFragSize, estIntSelCutFrag
 from .io import loops2juice, loops2washU, parseJd, parseRawBedpe, parseRawBedpe2
 from .utils import getLogger, mainHelp
 
@@ -90,6 +90,99 @@ def _single(f, eps, minPts, cut=0):
     if len(dataS) > 0:
         dss.append(d[in_s].astype(np.float64))
     return key, f, dataI, dataS, dis, (np.concatenate(dss) if dss else np.zeros(0, np.float64))
+
+
+def _moments(vals):
+    """(n, mean, M2) of log2(vals) in float64 on the device; vals: positive int32 CUDA tensor."""
+    import torch
+    n = int(vals.numel())
+    if n == 0:
+        return (0, 0.0, 0.0)
+    x = torch.log2(vals.to(torch.float64))
+    mean = x.mean()
+    return (n, float(mean), float(((x - mean) ** 2).sum()))
+
+
+def _single_stats(f, eps, minPts, cut=0):
+    """As _single, but the distance collections stay in HBM: returns the candidate records, the raw
+    sizes of dis / dss, their log2 moments and the positive self-ligation distances (device tensor)."""
+    import torch
+    ch = _Resident.get(f)
+    key = ch.key
+    dataI, dataS = [], []
+    dd = ch.dy - ch.dx                                   # Y - X on the device
+    empty = torch.zeros(0, dtype=torch.int32, device=dd.device)
+    removed = dd[dd < cut] if cut > 0 else empty
+    n_act = int(dd.numel() - removed.numel())
+    if n_act == 0:
+        pos = removed.abs()
+        pos = pos[pos > 0]
+        return key, f, dataI, dataS, 0, int(removed.numel()), (0, 0.0, 0.0), _moments(pos), pos
+    sys.stderr.write("Clustering %s and %s using eps as %s, minPts as %s,pre-set distance cutoff as > %s\n" %
+                     (key[0], key[1], eps, minPts, cut))
+    labels, info, bbox, size, kind, row_kind = device.cluster_and_summarise(ch.dx, ch.dy, int(eps), int(minPts), DBSCAN_VARIANT,
+                                                                           int(cut) if cut > 0 else 0)
+    bbox_h, kind_h = bbox.cpu().numpy(), kind.cpu().numpy()
+    for b in bbox_h[kind_h == 1].tolist():
+        dataI.append([key[0], b[0], b[1], key[1], b[2], b[3]])
+    for b in bbox_h[kind_h == 2].tolist():
+        dataS.append([key[0], b[0], b[1], key[1], b[2], b[3]])
+    inter = dd[row_kind == 1] if dataI else empty
+    selfm = dd[row_kind == 2] if dataS else empty
+    sys.stderr.write("Clustering %s and %s finished. Estimated %s self-ligation reads and %s inter-ligation reads\n" %
+                     (key[0], key[1], int(selfm.numel()), int(inter.numel())))
+    n_dis, n_dss = int(inter.numel()), int(removed.numel() + selfm.numel())
+    inter = inter.abs()
+    inter = inter[inter > 0]
+    selfd = torch.cat([removed, selfm]).abs()
+    selfd = selfd[selfd > 0]
+    return key, f, dataI, dataS, n_dis, n_dss, _moments(inter), _moments(selfd), selfd
+
+
+def _round(fs, eps, minPts, cut):
+    """One clustering round over all chromosomes with the cut-off statistics reduced on the GPU.
+    -> (dataI, dataS, n_dis, n_dss, cut_or_None)"""
+    import torch
+    mine = dist.my_share(fs)
+    full = {f: _single_stats(f, eps, minPts, cut) for f in mine}
+    part = {f: r[:8] for f, r in full.items()}           # small host objects travel through the object gather
+    ds = dist.merge_in_order(fs, part)
+    dataI, dataS, n_dis, n_dss, mi, ms = {}, [], 0, 0, [], []
+    used = set()
+    for f, d in zip(fs, ds):
+        if len(d[2]) == 0:                               # pipe.py:121-122: chromosomes without inter-ligation
+            continue                                     # clusters contribute nothing, not even their dss
+        used.add(f)
+        dataI[d[0]] = {"f": d[1], "records": d[2]}
+        dataS.extend(d[3])
+        n_dis += d[4]
+        n_dss += d[5]
+        mi.append(d[6])
+        ms.append(d[7])
+    if len(dataI) == 0 or n_dis == 0 or n_dss == 0:
+        return dataI, dataS, n_dis, n_dss, None
+    dev = torch.device("cuda", torch.cuda.current_device())
+    local = [full[f][8] for f in mine if f in used]
+    local = torch.cat(local) if local else torch.zeros(0, dtype=torch.int32, device=dev)
+    allself = dist.all_gather_concat(local)
+    srt = torch.sort(allself).values
+    k = int(srt.numel())
+    mid = srt[[(k - 1) // 2, k // 2]].cpu().tolist()
+    cut_2, frags = cut_from_moments(mi, ms, _TwoMiddle(k, mid))
+    return dataI, dataS, n_dis, n_dss, cut_2
+
+
+class _TwoMiddle:
+    """What cut_from_moments needs of the sorted self-ligation distances: length and the two middle values."""
+
+    def __init__(self, k, mid):
+        self.k, self.mid = k, mid
+
+    def __len__(self):
+        return self.k
+
+    def __getitem__(self, i):
+        return self.mid[0] if i == (self.k - 1) // 2 else self.mid[1]
 
 
 def singleDBSCAN(f, eps, minPts, cut=0):
@@ -196,14 +289,13 @@ def pipe(fs, fout, eps, minPts, chroms="", cpu=1, tmp=0, hic=0, washU=0, juice=0
     cuts = [cut]
     for ep in eps:
         for m in minPts:
-            dataI_2, dataS_2, dis_2, dss_2 = runDBSCAN(cfs, ep, m, cut, cpu)
+            dataI_2, dataS_2, n_dis, n_dss, cut_2 = _round(cfs, ep, m, cut)
             if len(dataI_2) == 0:
                 log.info("ERROR: no inter-ligation PETs detected for eps %s minPts %s,can't model the distance cutoff,continue anyway" % (ep, m))
                 continue
-            if len(dis_2) == 0 or len(dss_2) == 0:
+            if cut_2 is None:
                 dataI = combineTwice(dataI, dataI_2)
                 continue
-            cut_2, frags = estIntSelCutFrag(np.array(dis_2), np.array(dss_2))
             log.info("Estimated inter-ligation and self-ligation distance cutoff as %s for eps=%s,minPts=%s" % (cut_2, ep, m))
             cuts.append(cut_2)
             cut = cut_2

@@ -31,14 +31,14 @@ def test_pipe_m1_chr21(need_gpu, gold_dir, tmp_path, monkeypatch):
     _write_bedpe(bedpe, d["X"], d["Y"])
     monkeypatch.chdir(tmp_path)
     cuts = []
-    orig = pipe.estIntSelCutFrag
+    orig = pipe._round
 
-    def spy(di, ds, log=1):
-        r = orig(di, ds, log)
-        cuts.append((len(di), len(ds), r[0]))
+    def spy(fs, eps, minPts, cut):
+        r = orig(fs, eps, minPts, cut)
+        cuts.append((r[2], r[3], r[4]))
         return r
 
-    monkeypatch.setattr(pipe, "estIntSelCutFrag", spy)
+    monkeypatch.setattr(pipe, "_round", spy)
     pipe.pipe([bedpe], "out", [500, 1000, 2000], [5], cpu=1, tmp=1, hic=0, washU=1, juice=1)
     assert [c[2] for c in cuts] == [int(x) for x in gold["round_cut_out"]] == [4601, 13532, 11103]
     assert [c[0] for c in cuts] == [int(x) for x in gold["round_ndis"]]
@@ -64,6 +64,10 @@ def test_run_dbscan_round_records(need_gpu, gold_dir, tmp_path):
         assert np.array_equal(recs, gold["round%d_records" % k])
         assert len(dataS) == int(gold["round_nS"][k])
         assert (len(dis), len(dss)) == (int(gold["round_ndis"][k]), int(gold["round_ndss"][k]))
+        # host estimate (the reference's numpy path) and the device-side reduction give the same integer cut
+        host_cut = pipe.estIntSelCutFrag(np.array(dis), np.array(dss))[0]
+        _, _, n_dis, n_dss, dev_cut = pipe._round([f], eps, 5, cut)
+        assert (n_dis, n_dss, dev_cut) == (len(dis), len(dss), host_cut) and host_cut == int(gold["round_cut_out"][k])
 
 
 def test_getintsig_matches_reference_tuples(need_gpu, gold_dir, tmp_path):
@@ -99,8 +103,8 @@ def test_pipe_multi_chrom_hic(need_gpu, gold_dir, tmp_path, monkeypatch):
                 fh.write("%s\t%d\t%d\t%s\t%d\t%d\tp\t.\t+\t-\n" % (name, x, x, name, y, y))
     monkeypatch.chdir(tmp_path)
     cuts = []
-    orig = pipe.estIntSelCutFrag
-    monkeypatch.setattr(pipe, "estIntSelCutFrag", lambda di, ds, log=1: (cuts.append((len(di), len(ds), orig(di, ds, log)[0])), orig(di, ds, log))[1])
+    orig = pipe._round
+    monkeypatch.setattr(pipe, "_round", lambda fs, e, m, c: (lambda r: (cuts.append((r[2], r[3], r[4])), r)[1])(orig(fs, e, m, c)))
     pipe.pipe([bedpe], "out", [1000, 2000], [8, 5], cpu=1, tmp=0, hic=1)
     assert np.array_equal(np.array(cuts, np.int64), gold["cuts"])
     assert open(tmp_path / "out.loop", "rb").read() == open(os.path.join(gold_dir, "multi_hic.loop"), "rb").read()

@@ -30,6 +30,16 @@ def test_stats_tail_matches_reference_tuples(gold):
         assert tuple(float(x) for x in got) == tuple(float(x) for x in want), k
 
 
+def test_stats_batch_equals_scalar(gold):
+    N = int(gold["sig_N"])
+    c = gold["sig_ints200"].astype(np.int32)
+    batch = cModel._stats_batch(c, N)
+    for k in range(200):
+        one = cModel._stats(c[k], N)
+        assert tuple(float(b[k]) for b in batch) == tuple(float(x) for x in one), k
+        assert tuple(float(b[k]) for b in batch) == tuple(float(x) for x in gold["sig_tuples"][k][5:]), k
+
+
 def test_scoring_tail_reproduces_loop_file(gold, gold_dir, tmp_path):
     """From the reference's per-candidate tuples, the host tail (key numbering, removeDup x2,
     Bonferroni, markIntSig, to_csv) must reproduce the reference's .loop byte for byte."""
@@ -208,3 +218,21 @@ def test_facade_argument_contract():
         V2(np.zeros((4, 2), np.int64), 1000, 5)
     with pytest.raises(CloopsError):
         V2(np.zeros((4, 3), np.int64), 0.5, 5)
+
+
+def test_moment_combination_matches_numpy():
+    rng = np.random.default_rng(8)
+    for trial in range(20):
+        chunks = [rng.integers(1, 3_000_000, int(rng.integers(1, 4000))) for _ in range(int(rng.integers(1, 7)))]
+        parts = []
+        for c in chunks:
+            x = np.log2(c.astype(np.float64))
+            parts.append((len(x), float(x.mean()), float(((x - x.mean()) ** 2).sum())))
+        allx = np.log2(np.concatenate(chunks).astype(np.float64))
+        n, mean, std = ests.combine_moments(parts + [(0, 0.0, 0.0)])
+        assert n == len(allx) and abs(mean - allx.mean()) < 1e-12 and abs(std - allx.std()) < 1e-12
+    di = rng.integers(5000, 500000, 4001)
+    dsv = rng.integers(50, 3000, 6000)
+    mom = lambda v: (len(v), float(np.log2(v.astype(float)).mean()), float(((np.log2(v.astype(float)) - np.log2(v.astype(float)).mean()) ** 2).sum()))
+    assert ests.cut_from_moments([mom(di[:1000]), mom(di[1000:])], [mom(dsv[:10]), mom(dsv[10:])], np.sort(dsv)) == ests.estIntSelCutFrag(di, dsv)
+    assert ests.cut_from_moments([mom(di)], [mom(dsv[:5999])], np.sort(dsv[:5999])) == ests.estIntSelCutFrag(di, dsv[:5999])
