@@ -161,9 +161,12 @@ def _round(fs, eps, minPts, cut):
         ms.append(d[7])
     if len(dataI) == 0 or n_dis == 0 or n_dss == 0:
         return dataI, dataS, n_dis, n_dss, None
-    dev = torch.device("cuda", torch.cuda.current_device())
     local = [full[f][8] for f in mine if f in used]
-    local = torch.cat(local) if local else torch.zeros(0, dtype=torch.int32, device=dev)
+    if local:
+        local = torch.cat(local)
+    else:                                                 # this rank owns no contributing chromosome
+        dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+        local = torch.zeros(0, dtype=torch.int32, device=dev)
     allself = dist.all_gather_concat(local)
     srt = torch.sort(allself).values
     k = int(srt.numel())

@@ -51,3 +51,33 @@ if dist.rank() == 0:
     assert list(tab["significant"]) == [1.0] * 4
     open(os.path.join(out, "ok"), "w").write("ok")
 assert dist.broadcast_object({"cut": 4601} if dist.rank() == 0 else None) == {"cut": 4601}
+
+# device-side cut-off reduction across ranks (CPU tensors over gloo here, CUDA tensors over NCCL on the box)
+import torch  # noqa: E402
+
+from cloops_b200 import ests  # noqa: E402
+
+rng = np.random.default_rng(5)
+dist_i = {f: rng.integers(5000, 400000, 300 + 40 * k) for k, f in enumerate(files)}
+dist_s = {f: rng.integers(40, 3000, 500 + 70 * k) for k, f in enumerate(files)}
+
+
+def mom(v):
+    x = np.log2(v.astype(np.float64))
+    return (len(x), float(x.mean()), float(((x - x.mean()) ** 2).sum()))
+
+
+def fake_stats(f, eps, minPts, cut=0):
+    c = f.split("-")[0]
+    recs = [[c, 1, 2, c, 30, 40]] if c != "chrE" else []
+    return (c, c), f, recs, [], len(dist_i[f]), len(dist_s[f]), mom(dist_i[f]), mom(dist_s[f]), torch.from_numpy(dist_s[f].astype(np.int32))
+
+
+pipe._single_stats = fake_stats
+dataI, dataS, n_dis, n_dss, cut = pipe._round(files, 1000, 5, 0)
+used = files[:4]                                         # chrE has no inter-ligation records: excluded (pipe.py:121-122)
+want = ests.estIntSelCutFrag(np.concatenate([dist_i[f] for f in used]), np.concatenate([dist_s[f] for f in used]))[0]
+assert cut == want, (cut, want)
+assert n_dis == sum(len(dist_i[f]) for f in used) and n_dss == sum(len(dist_s[f]) for f in used)
+got = dist.all_gather_concat(torch.arange(3 + dist.rank(), dtype=torch.int32))
+assert got.tolist() == [0, 1, 2, 0, 1, 2, 3]
