@@ -109,3 +109,21 @@ def test_pipe_multi_chrom_hic(need_gpu, gold_dir, tmp_path, monkeypatch):
     assert np.array_equal(np.array(cuts, np.int64), gold["cuts"])
     assert open(tmp_path / "out.loop", "rb").read() == open(os.path.join(gold_dir, "multi_hic.loop"), "rb").read()
     assert not os.path.isdir(tmp_path / "out")       # temp .jd directory removed without -s
+
+
+def test_cli_main(need_gpu, gold_dir, tmp_path, monkeypatch):
+    """The ``cLoops`` command line (cLoops/pipe.py:298-352): -m 1 and the equivalent explicit lists."""
+    from cloops_b200 import pipe
+    d = np.load(os.path.join(gold_dir, "chr21_pets.npz"))
+    bedpe = str(tmp_path / "chr21.bedpe")
+    _write_bedpe(bedpe, d["X"], d["Y"])
+    monkeypatch.chdir(tmp_path)
+    want = open(os.path.join(gold_dir, "chr21_m1.loop"), "rb").read()
+    pipe.main(["-f", bedpe, "-o", "a", "-m", "1"])
+    assert open(tmp_path / "a.loop", "rb").read() == want
+    assert not os.path.isdir(tmp_path / "a")
+    pipe.main(["-f", bedpe, "-o", "b", "-eps", "2000,500,1000", "-minPts", "5", "-c", "chr21", "-s"])
+    assert open(tmp_path / "b.loop", "rb").read() == want
+    assert os.path.isdir(tmp_path / "b")
+    pipe.main(["-f", bedpe, "-o", "b", "-m", "1"])           # existing output directory: refuse, leave results alone
+    assert open(tmp_path / "b.loop", "rb").read() == want
