@@ -160,6 +160,7 @@ def workload_config(args, n_chrom):
     return {"workload": "synthetic ChIA-PET %d cis PETs, single chromosome, eps=%d minPts=%d (BASELINE.json configs[1]); "
                         "%d chromosome(s), one per GPU" % (args.pets, EPS, MINPTS, n_chrom),
             "clusterer": "cDBSCAN2", "scoring": "range counts (123 ints) of every inter-ligation candidate; scipy tail excluded",
+            "outputs": "candidate records, per-PET inter/self membership (index order), range counts (the returns of pipe.py:52-110 + cModel.py:118-143)",
             "l2": "256 MiB buffer written between timed steps", "pets_per_gpu": args.pets}
 
 

@@ -188,24 +188,43 @@ __global__ void __launch_bounds__(256) union_kernel(const u64* __restrict__ keys
 // full compression + per-component statistics.  Sorted order is spatially coherent, so lanes of a warp
 // mostly share a root: statistics are reduced per (warp, root) group before touching global atomics
 // (the giant diagonal component would otherwise serialise millions of same-address atomics).
+#define CMP_SLOTS 64
 __global__ void __launch_bounds__(256) compress_kernel(const u64* __restrict__ keys, const u32* __restrict__ rows, GridParams P,
                                                        Work W, int variant) {
+    // (warp, root) groups reduce in registers, their leaders in a small direct-mapped CTA table; only
+    // one partial per (CTA, root) -- or a table collision -- reaches the global atomics
+    __shared__ int s_root[CMP_SLOTS], s_cnt[CMP_SLOTS], s_min[CMP_SLOTS];
+    if (threadIdx.x < CMP_SLOTS) { s_root[threadIdx.x] = -1; s_cnt[threadIdx.x] = 0; s_min[threadIdx.x] = INT_MAX; }
+    __syncthreads();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool core = (i < P.n_act) && (keys[i] >> 63);
     if (i < P.n_act && !core) W.assigned[i] = -1;
     const unsigned cm = __ballot_sync(0xffffffffu, core);
-    if (!core) return;
-    int r = uf_find(W.parent, i);
-    W.parent[i] = r;
-    W.assigned[i] = r;
-    int rk = (variant == CLOOPS_V1) ? (int)rows[i] : W.cellmin[W.chead[i]];
-    const unsigned m = __match_any_sync(cm, r);
-    const int vmin = __reduce_min_sync(m, rk);
-    if ((int)(threadIdx.x & 31) == __ffs(m) - 1) {
-        atomicAdd(&W.ncore[r], __popc(m));
-        atomicMin(&W.rank[r], vmin);
+    if (core) {
+        int r = uf_find(W.parent, i);
+        W.parent[i] = r;
+        W.assigned[i] = r;
+        int rk = (variant == CLOOPS_V1) ? (int)rows[i] : W.cellmin[W.chead[i]];
+        const unsigned m = __match_any_sync(cm, r);
+        const int vmin = __reduce_min_sync(m, rk);
+        if ((int)(threadIdx.x & 31) == __ffs(m) - 1) {
+            const int slot = r & (CMP_SLOTS - 1);
+            const int prev = atomicCAS(&s_root[slot], -1, r);
+            if (prev == -1 || prev == r) {
+                atomicAdd(&s_cnt[slot], __popc(m));
+                atomicMin(&s_min[slot], vmin);
+            } else {
+                atomicAdd(&W.ncore[r], __popc(m));
+                atomicMin(&W.rank[r], vmin);
+            }
+        }
+        if (r == i) atomicAdd(&W.counters[4], 1);
     }
-    if (r == i) atomicAdd(&W.counters[4], 1);
+    __syncthreads();
+    if (threadIdx.x < CMP_SLOTS && s_root[threadIdx.x] >= 0) {
+        atomicAdd(&W.ncore[s_root[threadIdx.x]], s_cnt[threadIdx.x]);
+        atomicMin(&W.rank[s_root[threadIdx.x]], s_min[threadIdx.x]);
+    }
 }
 
 // parent[] of core points may still be one hop short for points compressed before their root was
@@ -354,6 +373,7 @@ __global__ void __launch_bounds__(256) number_flags_kernel(const u64* __restrict
     if (numbered) W.flags[W.rank[i]] = 1;
 }
 
+// labels == NULL skips the scatter to row order (callers that work in index order, e.g. the pipeline)
 __global__ void __launch_bounds__(256) label_kernel(const u32* __restrict__ rows, GridParams P, Work W, int variant, int minPts,
                                                     int* __restrict__ labels, int* __restrict__ labels_sorted) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -364,7 +384,7 @@ __global__ void __launch_bounds__(256) label_kernel(const u32* __restrict__ rows
             bool keep = (variant == CLOOPS_V1) ? (W.size[a] >= minPts) : (W.status[a] != ST_DEAD);
             if (keep) lab = W.ids[W.rank[a]];
         }
-        labels[rows[i]] = lab;
+        if (labels) labels[rows[i]] = lab;
         if (labels_sorted) labels_sorted[i] = lab;
     }
     block_count(W.slots_lab, lab >= 0);
@@ -376,7 +396,7 @@ int index_dbscan(cloops_index* ix, int minPts, int variant, int* d_labels, int* 
     if (variant != CLOOPS_V1 && variant != CLOOPS_V2) return fail(CLOOPS_EINVAL, "variant %d not served by the strip index", variant);
     if (h_info) for (int k = 0; k < 8; ++k) h_info[k] = 0;
     if (P.n == 0) return 0;
-    if (P.n_act < P.n) LAUNCH(fill_int_kernel, cdiv(P.n, 256), 256, 0, st, d_labels, -1, (long long)P.n);
+    if (d_labels && P.n_act < P.n) LAUNCH(fill_int_kernel, cdiv(P.n, 256), 256, 0, st, d_labels, -1, (long long)P.n);
     if (P.n_act == 0) return 0;
     const int na = P.n_act, g = cdiv(na, 256);
     Temp tmp(st);

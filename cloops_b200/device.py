@@ -81,24 +81,38 @@ def row_kinds_device(labels, kind) -> torch.Tensor:
     return out[:n]
 
 
-def cluster_and_summarise(dx, dy, eps: int, minPts: int, variant: int, cut: int = 0):
-    """labels (row order), info, bbox, size, kind, row_kind.  For v1/v2 the per-cluster reduction runs
-    in index order (spatially coherent: few distinct labels per warp), through the resident index."""
+class ClusterResult:
+    """Output of cluster_and_summarise.  Row-order members (labels, row_kind) are None when the caller
+    asked for index order only; index-order members (xs, ys, labels_sorted, kind_sorted) are None for
+    blockDBSCAN, which has no strip index."""
+    __slots__ = ("labels", "info", "bbox", "size", "kind", "row_kind", "xs", "ys", "labels_sorted", "kind_sorted")
+
+
+def cluster_and_summarise(dx, dy, eps: int, minPts: int, variant: int, cut: int = 0, rows: bool = True) -> ClusterResult:
+    """Cluster one chromosome and reduce the clusters to candidate records.  For v1/v2 the per-cluster
+    reduction runs in index order (spatially coherent: few distinct labels per warp) through the resident
+    index; ``rows=False`` skips every row-order output (label scatter, per-row kind)."""
+    r = ClusterResult()
+    r.xs = r.ys = r.labels_sorted = r.kind_sorted = None
     if variant == _lib.BLOCK:
-        labels, info = dbscan_device(dx, dy, eps, minPts, variant, cut)
-        return (labels, info) + tuple(cluster_summary_device(dx, dy, labels, info["n_clusters"]))
+        r.labels, r.info = dbscan_device(dx, dy, eps, minPts, variant, cut)
+        r.bbox, r.size, r.kind, r.row_kind = cluster_summary_device(dx, dy, r.labels, r.info["n_clusters"])
+        return r
     ix = Index(dx, dy, eps, cut)
     try:
-        labels, ls, info = ix.dbscan(minPts, variant, want_sorted=True)
+        r.labels, ls, r.info = ix.dbscan(minPts, variant, want_sorted=True, want_rows=rows)
         if ix.n_active:
-            xs, ys = ix.coords()
-            bbox, size, kind, _ = cluster_summary_device(xs, ys, ls, info["n_clusters"], want_row_kind=False)
+            r.xs, r.ys = ix.coords()
+            r.bbox, r.size, r.kind, _ = cluster_summary_device(r.xs, r.ys, ls, r.info["n_clusters"], want_row_kind=False)
         else:
-            bbox, size, kind, _ = cluster_summary_device(dx, dy, labels, 0, want_row_kind=False)
-        row_kind = row_kinds_device(labels, kind)
+            r.xs = r.ys = torch.zeros(0, dtype=torch.int32, device=dx.device)
+            r.bbox, r.size, r.kind, _ = cluster_summary_device(dx, dy, ls, 0, want_row_kind=False)
+        r.labels_sorted = ls
+        r.kind_sorted = row_kinds_device(ls, r.kind)
+        r.row_kind = row_kinds_device(r.labels, r.kind) if rows else None
     finally:
         ix.close()
-    return labels, info, bbox, size, kind, row_kind
+    return r
 
 
 class Index:
@@ -118,12 +132,13 @@ class Index:
         check(_lib.lib().cloops_index_count(self._h, int(cap), out.data_ptr(), _stream()))
         return out
 
-    def dbscan(self, minPts: int, variant: int, want_sorted: bool = False):
-        """labels (row order) [+ labels in index order] + info dict."""
-        labels = torch.empty(self.n, dtype=torch.int32, device=self._dx.device)
-        ls = torch.empty(max(self.n_active, 1), dtype=torch.int32, device=self._dx.device) if want_sorted else None
+    def dbscan(self, minPts: int, variant: int, want_sorted: bool = False, want_rows: bool = True):
+        """labels (row order, or None) [+ labels in index order] + info dict."""
+        dev = self._dx.device
+        labels = torch.empty(self.n, dtype=torch.int32, device=dev) if want_rows else None
+        ls = torch.empty(max(self.n_active, 1), dtype=torch.int32, device=dev) if want_sorted else None
         info = (C.c_int64 * 8)()
-        check(_lib.lib().cloops_index_dbscan(self._h, int(minPts), int(variant), labels.data_ptr(),
+        check(_lib.lib().cloops_index_dbscan(self._h, int(minPts), int(variant), labels.data_ptr() if want_rows else None,
                                              ls.data_ptr() if want_sorted else None, C.addressof(info), _stream()))
         info = dict(zip(INFO_KEYS, (int(v) for v in info)))
         return (labels, ls[:self.n_active], info) if want_sorted else (labels, info)

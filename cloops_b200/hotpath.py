@@ -13,15 +13,21 @@ from ._lib import check
 
 
 class HotPathResult:
-    __slots__ = ("labels", "info", "bbox", "size", "kind", "row_kind", "cand", "counts")
+    """labels / row_kind: row order (None unless rows=True); kind_sorted: per-PET kind in index order;
+    bbox, size, kind: per cluster id; cand, counts: per inter-ligation candidate (ascending id)."""
+    __slots__ = ("labels", "info", "bbox", "size", "kind", "row_kind", "kind_sorted", "cand", "counts")
 
 
 def run_device(dx: torch.Tensor, dy: torch.Tensor, eps: int, minPts: int, variant: int = _lib.V2, cut: int = 0,
-               score: bool = True) -> HotPathResult:
-    """Inputs and outputs resident in HBM.  ``counts`` is int32 [n_inter, 123] for the inter-ligation
-    candidates in ascending cluster-id order (cLoops/pipe.py:97, cModel.py:281-295)."""
+               score: bool = True, rows: bool = False) -> HotPathResult:
+    """Inputs and outputs resident in HBM.  What the reference's per-chromosome step returns
+    (cLoops/pipe.py:52-110: candidate records and the membership of dis / dss) plus the range counts of
+    every inter-ligation candidate, int32 [n_inter, 123] in ascending cluster-id order (pipe.py:97,
+    cModel.py:281-295).  Cluster labels in row order are produced only on request (``rows=True``)."""
+    c = device.cluster_and_summarise(dx, dy, eps, minPts, variant, cut, rows=rows or variant == _lib.BLOCK)
     r = HotPathResult()
-    r.labels, r.info, r.bbox, r.size, r.kind, r.row_kind = device.cluster_and_summarise(dx, dy, eps, minPts, variant, cut)
+    r.labels, r.info, r.bbox, r.size, r.kind, r.row_kind = c.labels, c.info, c.bbox, c.size, c.kind, c.row_kind
+    r.kind_sorted = c.kind_sorted if c.kind_sorted is not None else c.row_kind
     r.cand = r.counts = None
     if score:
         cand = r.bbox[r.kind == 1].clamp_(min=0)[:, [0, 1, 2, 3]].contiguous()     # max(0, .) of cModel.py:281-282
@@ -44,7 +50,6 @@ class HostStep:
         dev = torch.device("cuda", torch.cuda.current_device() if device_index is None else device_index)
         self.dx = torch.empty(n, dtype=torch.int32, device=dev)
         self.dy = torch.empty(n, dtype=torch.int32, device=dev)
-        self.h_row_kind = torch.empty(n, dtype=torch.uint8).pin_memory()
         self._pinned = {}
         self.h2d_bytes = 2 * 4 * n
         self.d2h_bytes = 0
@@ -64,10 +69,10 @@ class HostStep:
         self.dx.copy_(hx, non_blocking=True)
         self.dy.copy_(hy, non_blocking=True)
         r = run_device(self.dx, self.dy, eps, minPts, variant)
-        self.h_row_kind.copy_(r.row_kind, non_blocking=True)
+        kind_rows = self._out("kind_rows", r.kind_sorted)
         bbox = self._out("bbox", r.bbox)
         kind = self._out("kind", r.kind)
         counts = self._out("counts", r.counts)
         torch.cuda.current_stream().synchronize()
-        self.d2h_bytes = self.h_row_kind.numel() + bbox.numel() * 4 + kind.numel() + counts.numel() * 4
-        return bbox, kind, counts, self.h_row_kind
+        self.d2h_bytes = kind_rows.numel() + bbox.numel() * 4 + kind.numel() + counts.numel() * 4
+        return bbox, kind, counts, kind_rows

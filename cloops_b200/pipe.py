@@ -75,9 +75,8 @@ def _single(f, eps, minPts, cut=0):
         return key, f, dataI, dataS, dis, (np.concatenate(dss) if dss else np.zeros(0, np.float64))
     sys.stderr.write("Clustering %s and %s using eps as %s, minPts as %s,pre-set distance cutoff as > %s\n" %
                      (key[0], key[1], eps, minPts, cut))
-    labels, info, bbox, size, kind, row_kind = device.cluster_and_summarise(ch.dx, ch.dy, int(eps), int(minPts), DBSCAN_VARIANT,
-                                                                           int(cut) if cut > 0 else 0)
-    bbox, kind, row_kind = bbox.cpu().numpy(), kind.cpu().numpy(), row_kind.cpu().numpy()
+    c = device.cluster_and_summarise(ch.dx, ch.dy, int(eps), int(minPts), DBSCAN_VARIANT, int(cut) if cut > 0 else 0)
+    bbox, kind, row_kind = c.bbox.cpu().numpy(), c.kind.cpu().numpy(), c.row_kind.cpu().numpy()
     for b in bbox[kind == 1].tolist():
         dataI.append([key[0], b[0], b[1], key[1], b[2], b[3]])
     for b in bbox[kind == 2].tolist():
@@ -120,15 +119,18 @@ def _single_stats(f, eps, minPts, cut=0):
         return key, f, dataI, dataS, 0, int(removed.numel()), (0, 0.0, 0.0), _moments(pos), pos
     sys.stderr.write("Clustering %s and %s using eps as %s, minPts as %s,pre-set distance cutoff as > %s\n" %
                      (key[0], key[1], eps, minPts, cut))
-    labels, info, bbox, size, kind, row_kind = device.cluster_and_summarise(ch.dx, ch.dy, int(eps), int(minPts), DBSCAN_VARIANT,
-                                                                           int(cut) if cut > 0 else 0)
-    bbox_h, kind_h = bbox.cpu().numpy(), kind.cpu().numpy()
+    c = device.cluster_and_summarise(ch.dx, ch.dy, int(eps), int(minPts), DBSCAN_VARIANT, int(cut) if cut > 0 else 0, rows=False)
+    bbox_h, kind_h = c.bbox.cpu().numpy(), c.kind.cpu().numpy()
+    if c.kind_sorted is not None:                        # index order: distances straight from the sorted coordinates
+        members, member_kind = c.ys - c.xs, c.kind_sorted
+    else:                                                # blockDBSCAN: row order
+        members, member_kind = dd, c.row_kind
     for b in bbox_h[kind_h == 1].tolist():
         dataI.append([key[0], b[0], b[1], key[1], b[2], b[3]])
     for b in bbox_h[kind_h == 2].tolist():
         dataS.append([key[0], b[0], b[1], key[1], b[2], b[3]])
-    inter = dd[row_kind == 1] if dataI else empty
-    selfm = dd[row_kind == 2] if dataS else empty
+    inter = members[member_kind == 1] if dataI else empty
+    selfm = members[member_kind == 2] if dataS else empty
     sys.stderr.write("Clustering %s and %s finished. Estimated %s self-ligation reads and %s inter-ligation reads\n" %
                      (key[0], key[1], int(selfm.numel()), int(inter.numel())))
     n_dis, n_dss = int(inter.numel()), int(removed.numel() + selfm.numel())

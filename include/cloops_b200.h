@@ -87,8 +87,9 @@ CLOOPS_API void cloops_index_free(cloops_index* ix);
 CLOOPS_API int64_t cloops_index_n_active(const cloops_index* ix);
 /* one launch of the region-query kernel over the index; d_counts_sorted int32[n_active] in index order */
 CLOOPS_API int cloops_index_count(cloops_index* ix, int32_t cap, int32_t* d_counts_sorted, void* stream);
-/* labels for one minPts over a built index (v1/v2 only).  d_labels: row order (as cloops_dbscan);
- * d_labels_sorted (may be NULL): int32[n_active], the same labels in index order. */
+/* labels for one minPts over a built index (v1/v2 only).  d_labels (may be NULL): row order, as
+ * cloops_dbscan; d_labels_sorted (may be NULL): int32[n_active], the same labels in index order.  Passing
+ * d_labels = NULL skips the scatter back to row order for callers that stay in index order. */
 CLOOPS_API int cloops_index_dbscan(cloops_index* ix, int32_t minPts, int32_t variant, int32_t* d_labels,
                         int32_t* d_labels_sorted, int64_t* h_info, void* stream);
 /* X, Y of the active PETs in index order (int32[n_active] each), decoded from the packed keys.  Index
