@@ -33,6 +33,7 @@ _SIGNATURES = {
     "cloops_neighbour_counts": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
     "cloops_index_build": (C.c_int, [_vp, _vp, _i64, _i32, _i32, C.POINTER(_vp), _vp]),
     "cloops_index_free": (None, [_vp]),
+    "cloops_index_release": (None, [_vp, _vp]),
     "cloops_index_n_active": (_i64, [_vp]),
     "cloops_index_count": (C.c_int, [_vp, _i32, _vp, _vp]),
     "cloops_index_dbscan": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _vp]),
@@ -41,6 +42,7 @@ _SIGNATURES = {
     "cloops_cluster_summary": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "cloops_coverage_build": (C.c_int, [_vp, _vp, _i64, C.POINTER(_vp), _vp]),
     "cloops_coverage_free": (None, [_vp]),
+    "cloops_coverage_release": (None, [_vp, _vp]),
     "cloops_range_counts": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "cloops_region_pets": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
 }

@@ -55,6 +55,8 @@ int cloops_index_build(const int32_t* d_x, const int32_t* d_y, int64_t n, int32_
 
 void cloops_index_free(cloops_index* ix) { index_free(ix, 0); }
 
+void cloops_index_release(cloops_index* ix, void* stream) { index_free(ix, (cudaStream_t)stream); }
+
 int64_t cloops_index_n_active(const cloops_index* ix) { return ix ? ix->P.n_act : 0; }
 
 int cloops_index_count(cloops_index* ix, int32_t cap, int32_t* d_counts_sorted, void* stream) {

@@ -211,14 +211,17 @@ int cloops_coverage_build(const int32_t* d_x, const int32_t* d_y, int64_t n, clo
     return stages_end(st);
 }
 
-void cloops_coverage_free(cloops_coverage* cov) {
+void cloops_coverage_release(cloops_coverage* cov, void* stream) {
     if (!cov) return;
-    if (cov->xs_x) cudaFreeAsync(cov->xs_x, 0);
-    if (cov->xs_y) cudaFreeAsync(cov->xs_y, 0);
-    if (cov->ys_y) cudaFreeAsync(cov->ys_y, 0);
-    if (cov->ys_x) cudaFreeAsync(cov->ys_x, 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cov->xs_x) cudaFreeAsync(cov->xs_x, st);
+    if (cov->xs_y) cudaFreeAsync(cov->xs_y, st);
+    if (cov->ys_y) cudaFreeAsync(cov->ys_y, st);
+    if (cov->ys_x) cudaFreeAsync(cov->ys_x, st);
     delete cov;
 }
+
+void cloops_coverage_free(cloops_coverage* cov) { cloops_coverage_release(cov, 0); }
 
 int cloops_range_counts(const cloops_coverage* cov, const int32_t* d_cand, int64_t m, int32_t* d_out, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;

@@ -152,8 +152,7 @@ class Index:
 
     def close(self):
         if getattr(self, "_h", None):
-            torch.cuda.current_stream().synchronize()
-            _lib.lib().cloops_index_free(self._h)
+            _lib.lib().cloops_index_release(self._h, _stream())       # stream-ordered: no host sync
             self._h = None
 
     def __del__(self):
@@ -198,8 +197,7 @@ class Coverage:
 
     def close(self):
         if getattr(self, "_h", None):
-            torch.cuda.current_stream().synchronize()
-            _lib.lib().cloops_coverage_free(self._h)
+            _lib.lib().cloops_coverage_release(self._h, _stream())    # stream-ordered: no host sync
             self._h = None
 
     def __del__(self):

@@ -83,7 +83,8 @@ CLOOPS_API int cloops_neighbour_counts(const int32_t* d_x, const int32_t* d_y, i
 typedef struct cloops_index cloops_index;
 CLOOPS_API int cloops_index_build(const int32_t* d_x, const int32_t* d_y, int64_t n, int32_t eps, int32_t cut,
                        cloops_index** out, void* stream);
-CLOOPS_API void cloops_index_free(cloops_index* ix);
+CLOOPS_API void cloops_index_free(cloops_index* ix);                 /* frees on the legacy default stream */
+CLOOPS_API void cloops_index_release(cloops_index* ix, void* stream);  /* stream-ordered free, no host sync */
 CLOOPS_API int64_t cloops_index_n_active(const cloops_index* ix);
 /* one launch of the region-query kernel over the index; d_counts_sorted int32[n_active] in index order */
 CLOOPS_API int cloops_index_count(cloops_index* ix, int32_t cap, int32_t* d_counts_sorted, void* stream);
@@ -115,6 +116,7 @@ CLOOPS_API int cloops_row_kinds(const int32_t* d_labels, int64_t n, const uint8_
 typedef struct cloops_coverage cloops_coverage;
 CLOOPS_API int cloops_coverage_build(const int32_t* d_x, const int32_t* d_y, int64_t n, cloops_coverage** out, void* stream);
 CLOOPS_API void cloops_coverage_free(cloops_coverage* cov);
+CLOOPS_API void cloops_coverage_release(cloops_coverage* cov, void* stream);  /* stream-ordered free */
 /* d_cand int32[m,4] = iva0, iva1, ivb0, ivb1 (already clamped at 0, cModel.py:281-282);
  * d_out int32[m,123] = ra, rb, rab, na[10], nb[10], C[10][10] row-major (i over A windows). */
 CLOOPS_API int cloops_range_counts(const cloops_coverage* cov, const int32_t* d_cand, int64_t m, int32_t* d_out, void* stream);
