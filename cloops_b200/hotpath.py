@@ -12,6 +12,16 @@ from . import _lib, device
 from ._lib import check
 
 
+_SIDE = {}
+
+
+def _side_stream(dev) -> "torch.cuda.Stream":
+    key = (dev.type, dev.index)
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=dev)
+    return _SIDE[key]
+
+
 class HotPathResult:
     """labels / row_kind: row order (None unless rows=True); kind_sorted: per-PET kind in index order;
     bbox, size, kind: per cluster id; cand, counts: per inter-ligation candidate (ascending id)."""
@@ -24,6 +34,15 @@ def run_device(dx: torch.Tensor, dy: torch.Tensor, eps: int, minPts: int, varian
     (cLoops/pipe.py:52-110: candidate records and the membership of dis / dss) plus the range counts of
     every inter-ligation candidate, int32 [n_inter, 123] in ascending cluster-id order (pipe.py:97,
     cModel.py:281-295).  Cluster labels in row order are produced only on request (``rows=True``)."""
+    # The coverage model (two radix sorts) does not depend on the clustering: build it on a side stream
+    # while the latency-bound clustering kernels (union-find, border passes) run on the main stream.
+    main = torch.cuda.current_stream()
+    cov = None
+    if score:
+        side = _side_stream(dx.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            cov = device.Coverage(dx, dy)
     c = device.cluster_and_summarise(dx, dy, eps, minPts, variant, cut, rows=rows or variant == _lib.BLOCK)
     r = HotPathResult()
     r.labels, r.info, r.bbox, r.size, r.kind, r.row_kind = c.labels, c.info, c.bbox, c.size, c.kind, c.row_kind
@@ -32,10 +51,10 @@ def run_device(dx: torch.Tensor, dy: torch.Tensor, eps: int, minPts: int, varian
     if score:
         cand = r.bbox[r.kind == 1].clamp_(min=0)[:, [0, 1, 2, 3]].contiguous()     # max(0, .) of cModel.py:281-282
         m = cand.shape[0]
-        cov = device.Coverage(dx, dy)
+        main.wait_stream(side)
         out = torch.empty((max(m, 1), 123), dtype=torch.int32, device=dx.device)
         if m:
-            check(_lib.lib().cloops_range_counts(cov._h, cand.data_ptr(), m, out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+            check(_lib.lib().cloops_range_counts(cov._h, cand.data_ptr(), m, out.data_ptr(), main.cuda_stream))
         cov.close()
         r.cand, r.counts = cand, out[:m]
     return r
