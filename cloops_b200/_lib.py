@@ -45,6 +45,12 @@ _SIGNATURES = {
     "cloops_coverage_release": (None, [_vp, _vp]),
     "cloops_range_counts": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "cloops_region_pets": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    "cloops_pass_run": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, C.POINTER(_vp), _vp]),
+    "cloops_pass_run_host": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, C.POINTER(_vp), _vp]),
+    "cloops_pass_sizes": (C.c_int, [_vp, _vp, _vp]),
+    "cloops_pass_device_ptr": (_vp, [_vp, C.c_int]),
+    "cloops_pass_fetch": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "cloops_pass_free": (None, [_vp, _vp]),
 }
 
 EXPORTS = tuple(_SIGNATURES)

@@ -99,14 +99,15 @@ __device__ __forceinline__ int upper_bound_i(const int* __restrict__ a, int n, i
 template <int WIN>
 __global__ void __launch_bounds__(32 * RC_WARPS) range_count_kernel(const int* __restrict__ xs_x, const int* __restrict__ xs_y,
                                                                     const int* __restrict__ ys_y, const int* __restrict__ ys_x, int n,
-                                                                    const int* __restrict__ cand, long long ncand, int* __restrict__ out) {
+                                                                    const int* __restrict__ cand, long long ncand, const int* __restrict__ d_ncand,
+                                                                    int* __restrict__ out) {
     constexpr int NOUT = (WIN > 0) ? 123 : 3;
     constexpr int NWIN = (WIN > 0) ? NW : 1;
     __shared__ Windows Ws[RC_WARPS];
     __shared__ int accs[RC_WARPS][NOUT];
     const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long m = (long long)blockIdx.x * RC_WARPS + wl;
-    if (m >= ncand) return;                                    // whole warp
+    if (m >= ncand || (d_ncand && m >= *d_ncand)) return;      // whole warp
     Windows& W = Ws[wl];
     int* acc = accs[wl];
     for (int t = lane; t < NOUT; t += 32) acc[t] = 0;
@@ -173,7 +174,8 @@ __global__ void __launch_bounds__(32 * RC_WARPS) range_count_kernel(const int* _
 
 using namespace cloops;
 
-static int coverage_build(const int32_t* d_x, const int32_t* d_y, int64_t n, cloops_coverage** out, cudaStream_t st) {
+namespace cloops {
+int coverage_build(const int32_t* d_x, const int32_t* d_y, int64_t n, cloops_coverage** out, cudaStream_t st) {
     if (n < 0 || n > 0x7fffff00LL) return fail(CLOOPS_EINVAL, "n=%lld out of range", (long long)n);
     RET_IF(pool_init());
     cloops_coverage* cov = new cloops_coverage();
@@ -193,6 +195,17 @@ static int coverage_build(const int32_t* d_x, const int32_t* d_y, int64_t n, clo
     CU_TRY(cub::DeviceRadixSort::SortPairs(d_tmp, bytes, d_y, cov->ys_y, d_x, cov->ys_x, (int)n, 0, 32, st));
     return 0;
 }
+
+// d_ncand != NULL: the candidate count is read on the device (no host round trip); ncand is then an upper bound
+int range_counts_dev(const cloops_coverage* cov, const int32_t* d_cand, int64_t ncand, const int* d_ncand, int32_t* d_out,
+                     cudaStream_t st) {
+    if (ncand <= 0) return 0;
+    if (cov->n == 0) { CU_TRY(cudaMemsetAsync(d_out, 0, (size_t)ncand * 123 * sizeof(int), st)); return 0; }
+    LAUNCH(range_count_kernel<5>, (unsigned)((ncand + RC_WARPS - 1) / RC_WARPS), 32 * RC_WARPS, 0, st, cov->xs_x, cov->xs_y, cov->ys_y,
+           cov->ys_x, cov->n, d_cand, (long long)ncand, d_ncand, d_out);
+    return 0;
+}
+}  // namespace cloops
 
 extern "C" {
 
@@ -230,7 +243,7 @@ int cloops_range_counts(const cloops_coverage* cov, const int32_t* d_cand, int64
     stages_begin(st);
     if (m > 0) {
         if (cov->n == 0) CU_TRY(cudaMemsetAsync(d_out, 0, (size_t)m * 123 * sizeof(int), st));
-        else LAUNCH(range_count_kernel<5>, (unsigned)((m + RC_WARPS - 1) / RC_WARPS), 32 * RC_WARPS, 0, st, cov->xs_x, cov->xs_y, cov->ys_y, cov->ys_x, cov->n, d_cand, (long long)m, d_out);
+        else LAUNCH(range_count_kernel<5>, (unsigned)((m + RC_WARPS - 1) / RC_WARPS), 32 * RC_WARPS, 0, st, cov->xs_x, cov->xs_y, cov->ys_y, cov->ys_x, cov->n, d_cand, (long long)m, (const int*)nullptr, d_out);
     }
     stage_mark("range_counts", st);
     return stages_end(st);
@@ -243,7 +256,7 @@ int cloops_region_pets(const cloops_coverage* cov, const int32_t* d_cand, int64_
     stages_begin(st);
     if (m > 0) {
         if (cov->n == 0) CU_TRY(cudaMemsetAsync(d_out, 0, (size_t)m * 3 * sizeof(int), st));
-        else LAUNCH(range_count_kernel<0>, (unsigned)((m + RC_WARPS - 1) / RC_WARPS), 32 * RC_WARPS, 0, st, cov->xs_x, cov->xs_y, cov->ys_y, cov->ys_x, cov->n, d_cand, (long long)m, d_out);
+        else LAUNCH(range_count_kernel<0>, (unsigned)((m + RC_WARPS - 1) / RC_WARPS), 32 * RC_WARPS, 0, st, cov->xs_x, cov->xs_y, cov->ys_y, cov->ys_x, cov->n, d_cand, (long long)m, (const int*)nullptr, d_out);
     }
     stage_mark("region_pets", st);
     return stages_end(st);

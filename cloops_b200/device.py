@@ -205,3 +205,72 @@ class Coverage:
             self.close()
         except Exception:
             pass
+
+
+class _DevView:
+    """A device buffer owned by the C library, exposed through the CUDA array interface."""
+
+    def __init__(self, ptr, shape, typestr, owner):
+        self._owner = owner            # keeps the pass alive while a tensor aliases its memory
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+class Pass:
+    """One pass of the whole hot path over one chromosome in ONE C-ABI call (cloops_pass_run /
+    cloops_pass_run_host): clustering, candidate records, per-PET inter/self membership, coverage model and
+    range counts.  Attributes are zero-copy CUDA tensors over buffers owned by the pass."""
+
+    _WHICH = {"bbox": (0, "<i4"), "size": (1, "<i4"), "kind": (2, "|u1"), "xs": (3, "<i4"), "ys": (4, "<i4"),
+              "labels_sorted": (5, "<i4"), "member_kind": (6, "|u1"), "cand": (7, "<i4"), "counts": (8, "<i4")}
+
+    def __init__(self, x, y, eps: int, minPts: int, variant: int = _lib.V2, cut: int = 0, score: bool = True, host: bool = False):
+        require_cuda()
+        self._keep = (x, y)
+        n = x.numel()
+        h = C.c_void_p()
+        fn = _lib.lib().cloops_pass_run_host if host else _lib.lib().cloops_pass_run
+        check(fn(x.data_ptr(), y.data_ptr(), n, int(eps), int(minPts), int(cut), int(variant), 1 if score else 0, C.byref(h), _stream()))
+        self._h = h
+        sizes, info = (C.c_int64 * 6)(), (C.c_int64 * 8)()
+        check(_lib.lib().cloops_pass_sizes(h, C.addressof(sizes), C.addressof(info)))
+        self.n_members, self.n_clusters, self.n_candidates, self.scored, self.n_rows = (int(v) for v in sizes[:5])
+        self.info = dict(zip(INFO_KEYS, (int(v) for v in info)))
+        self._dev = torch.device("cuda", torch.cuda.current_device())
+
+    def _view(self, name: str) -> torch.Tensor:
+        which, typestr = self._WHICH[name]
+        k, nm, m = self.n_clusters, self.n_members, self.n_candidates
+        shape = {"bbox": (k, 4), "size": (k,), "kind": (k,), "xs": (nm,), "ys": (nm,), "labels_sorted": (nm,),
+                 "member_kind": (nm,), "cand": (m, 4), "counts": (m, 123)}[name]
+        dt = torch.int32 if typestr == "<i4" else torch.uint8
+        if 0 in shape:
+            return torch.zeros(shape, dtype=dt, device=self._dev)
+        ptr = _lib.lib().cloops_pass_device_ptr(self._h, which)
+        if not ptr:
+            return torch.zeros((0,) + tuple(shape[1:]), dtype=dt, device=self._dev)
+        return torch.as_tensor(_DevView(ptr, shape, typestr, self), device=self._dev)
+
+    def __getattr__(self, name):
+        if name in Pass._WHICH:
+            t = self._view(name)
+            self.__dict__[name] = t
+            return t
+        raise AttributeError(name)
+
+    def fetch(self, h_bbox=None, h_kind=None, h_member_kind=None, h_counts=None) -> None:
+        """D2H copies into (pinned) host tensors, one synchronisation."""
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        check(_lib.lib().cloops_pass_fetch(self._h, ptr(h_bbox), ptr(h_kind), ptr(h_member_kind), ptr(h_counts), _stream()))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            for name in Pass._WHICH:
+                self.__dict__.pop(name, None)
+            _lib.lib().cloops_pass_free(self._h, _stream())
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -28,8 +28,8 @@ class HotPathResult:
     __slots__ = ("labels", "info", "bbox", "size", "kind", "row_kind", "kind_sorted", "cand", "counts")
 
 
-def run_device(dx: torch.Tensor, dy: torch.Tensor, eps: int, minPts: int, variant: int = _lib.V2, cut: int = 0,
-               score: bool = True, rows: bool = False) -> HotPathResult:
+def run_device_separate(dx: torch.Tensor, dy: torch.Tensor, eps: int, minPts: int, variant: int = _lib.V2, cut: int = 0,
+                        score: bool = True, rows: bool = False) -> HotPathResult:
     """Inputs and outputs resident in HBM.  What the reference's per-chromosome step returns
     (cLoops/pipe.py:52-110: candidate records and the membership of dis / dss) plus the range counts of
     every inter-ligation candidate, int32 [n_inter, 123] in ascending cluster-id order (pipe.py:97,
@@ -60,38 +60,43 @@ def run_device(dx: torch.Tensor, dy: torch.Tensor, eps: int, minPts: int, varian
     return r
 
 
+def run_device(dx: torch.Tensor, dy: torch.Tensor, eps: int, minPts: int, variant: int = _lib.V2, cut: int = 0,
+               score: bool = True) -> "device.Pass":
+    """The same pass through the single C-ABI entry point ``cloops_pass_run``; returns the resident
+    ``device.Pass`` (bbox, size, kind, cand, counts, xs, ys, labels_sorted, member_kind, info)."""
+    return device.Pass(dx, dy, eps, minPts, variant, cut, score=score)
+
+
 class HostStep:
     """The same pass from HOST buffers: pinned int32 X, Y in; candidate records, per-PET kind bytes and
-    range counts out.  Device staging buffers and pinned result buffers are allocated once and re-used;
-    all copies are asynchronous on the current stream with one synchronisation at the end."""
+    range counts out, through the host entry points of the C ABI.  Pinned result buffers are allocated
+    once and re-used; one synchronisation at the end."""
 
     def __init__(self, n: int, device_index: int | None = None):
-        dev = torch.device("cuda", torch.cuda.current_device() if device_index is None else device_index)
-        self.dx = torch.empty(n, dtype=torch.int32, device=dev)
-        self.dy = torch.empty(n, dtype=torch.int32, device=dev)
         self._pinned = {}
         self.h2d_bytes = 2 * 4 * n
         self.d2h_bytes = 0
 
-    def _out(self, name: str, t: torch.Tensor) -> torch.Tensor:
-        """Pinned host buffer (grown geometrically) receiving an async copy of device tensor t."""
-        need = t.numel()
-        buf = self._pinned.get(name)
-        if buf is None or buf.numel() < need or buf.dtype != t.dtype:
-            buf = torch.empty(max(need * 2, 1024), dtype=t.dtype).pin_memory()
-            self._pinned[name] = buf
-        view = buf[:need].view(t.shape)
-        view.copy_(t, non_blocking=True)
-        return view
-
     def __call__(self, hx: torch.Tensor, hy: torch.Tensor, eps: int, minPts: int, variant: int = _lib.V2):
-        self.dx.copy_(hx, non_blocking=True)
-        self.dy.copy_(hy, non_blocking=True)
-        r = run_device(self.dx, self.dy, eps, minPts, variant)
-        kind_rows = self._out("kind_rows", r.kind_sorted)
-        bbox = self._out("bbox", r.bbox)
-        kind = self._out("kind", r.kind)
-        counts = self._out("counts", r.counts)
-        torch.cuda.current_stream().synchronize()
-        self.d2h_bytes = kind_rows.numel() + bbox.numel() * 4 + kind.numel() + counts.numel() * 4
-        return bbox, kind, counts, kind_rows
+        """cloops_pass_run_host (H2D of the pinned coordinates + the whole pass) and cloops_pass_fetch
+        (D2H of records, per-PET membership and range counts into pinned buffers, one synchronisation)."""
+        p = device.Pass(hx, hy, eps, minPts, variant, 0, score=True, host=True)
+        bbox = self._buf("bbox", (p.n_clusters, 4), torch.int32)
+        kind = self._buf("kind", (p.n_clusters,), torch.uint8)
+        members = self._buf("members", (p.n_members,), torch.uint8)
+        counts = self._buf("counts", (p.n_candidates, 123), torch.int32)
+        p.fetch(bbox, kind, members, counts)
+        self.d2h_bytes = members.numel() + bbox.numel() * 4 + kind.numel() + counts.numel() * 4
+        self.info = p.info
+        p.close()
+        return bbox, kind, counts, members
+
+    def _buf(self, name: str, shape, dtype) -> torch.Tensor:
+        need = 1
+        for d in shape:
+            need *= d
+        buf = self._pinned.get(name)
+        if buf is None or buf.numel() < need or buf.dtype != dtype:
+            buf = torch.empty(max(need * 2, 1024), dtype=dtype).pin_memory()
+            self._pinned[name] = buf
+        return buf[:need].view(shape)

@@ -119,12 +119,9 @@ def _single_stats(f, eps, minPts, cut=0):
         return key, f, dataI, dataS, 0, int(removed.numel()), (0, 0.0, 0.0), _moments(pos), pos
     sys.stderr.write("Clustering %s and %s using eps as %s, minPts as %s,pre-set distance cutoff as > %s\n" %
                      (key[0], key[1], eps, minPts, cut))
-    c = device.cluster_and_summarise(ch.dx, ch.dy, int(eps), int(minPts), DBSCAN_VARIANT, int(cut) if cut > 0 else 0, rows=False)
-    bbox_h, kind_h = c.bbox.cpu().numpy(), c.kind.cpu().numpy()
-    if c.kind_sorted is not None:                        # index order: distances straight from the sorted coordinates
-        members, member_kind = c.ys - c.xs, c.kind_sorted
-    else:                                                # blockDBSCAN: row order
-        members, member_kind = dd, c.row_kind
+    p = device.Pass(ch.dx, ch.dy, int(eps), int(minPts), DBSCAN_VARIANT, int(cut) if cut > 0 else 0, score=False)
+    bbox_h, kind_h = p.bbox.cpu().numpy(), p.kind.cpu().numpy()
+    members, member_kind = p.ys - p.xs, p.member_kind         # Y - X of every clustered PET, its cluster's kind
     for b in bbox_h[kind_h == 1].tolist():
         dataI.append([key[0], b[0], b[1], key[1], b[2], b[3]])
     for b in bbox_h[kind_h == 2].tolist():
@@ -138,6 +135,7 @@ def _single_stats(f, eps, minPts, cut=0):
     inter = inter[inter > 0]
     selfd = torch.cat([removed, selfm]).abs()
     selfd = selfd[selfd > 0]
+    p.close()
     return key, f, dataI, dataS, n_dis, n_dss, _moments(inter), _moments(selfd), selfd
 
 

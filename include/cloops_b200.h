@@ -123,6 +123,30 @@ CLOOPS_API int cloops_range_counts(const cloops_coverage* cov, const int32_t* d_
 /* only ra, rb, rab (getPETsforRegions, cModel.py:72-80): d_out int32[m,3] */
 CLOOPS_API int cloops_region_pets(const cloops_coverage* cov, const int32_t* d_cand, int64_t m, int32_t* d_out, void* stream);
 
+/* ---- one pass of the whole hot path over one chromosome, as ONE call ----------------------------------
+ * cluster (pipe.py:52-75) -> candidate records + dis/dss membership (pipe.py:76-109) -> coverage model
+ * (cModel.py:45-57) -> range counts of every inter-ligation candidate (cModel.py:118-143, skipped when
+ * score = 0).  Results stay in HBM inside the opaque pass object; the coverage build overlaps the
+ * clustering on an internal side stream.  cloops_pass_run_host starts from HOST coordinates (int32[n]
+ * each, pinned or pageable) and copies them in first: it is the end-to-end entry point. */
+typedef struct cloops_pass cloops_pass;
+CLOOPS_API int cloops_pass_run(const int32_t* d_x, const int32_t* d_y, int64_t n, int32_t eps, int32_t minPts, int32_t cut,
+                    int32_t variant, int32_t score, cloops_pass** out, void* stream);
+CLOOPS_API int cloops_pass_run_host(const int32_t* h_x, const int32_t* h_y, int64_t n, int32_t eps, int32_t minPts, int32_t cut,
+                         int32_t variant, int32_t score, cloops_pass** out, void* stream);
+/* sizes int64[6] = n_members, n_clusters, n_candidates, scored, n_rows, 0 ; h_info int64[8] as cloops_dbscan.
+ * Members are the clustered PETs in index order (rows in file order for CLOOPS_BLOCK). */
+CLOOPS_API int cloops_pass_sizes(const cloops_pass* p, int64_t* sizes, int64_t* h_info);
+/* device views valid until cloops_pass_free.  which: 0 bbox int32[k,4] (minX,maxX,minY,maxY per cluster id),
+ * 1 size int32[k], 2 kind u8[k] (0 dropped, 1 inter-ligation, 2 self-ligation), 3 xs int32[n_members],
+ * 4 ys int32[n_members], 5 labels int32[n_members], 6 member_kind u8[n_members], 7 cand int32[m,4] (clamped
+ * iva0,iva1,ivb0,ivb1 in ascending cluster id), 8 counts int32[m,123] */
+CLOOPS_API const void* cloops_pass_device_ptr(const cloops_pass* p, int which);
+/* copy results into HOST buffers (each may be NULL) and synchronise the stream once */
+CLOOPS_API int cloops_pass_fetch(const cloops_pass* p, int32_t* h_bbox, uint8_t* h_kind, uint8_t* h_member_kind, int32_t* h_counts,
+                      void* stream);
+CLOOPS_API void cloops_pass_free(cloops_pass* p, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
