@@ -61,14 +61,25 @@ __global__ void __launch_bounds__(256) cand_scatter_kernel(const unsigned char* 
     if (c == k - 1) *d_m = pos[c] + (kind[c] == 1 ? 1 : 0);
 }
 
-static thread_local cudaStream_t g_side = nullptr;
-static thread_local cudaEvent_t g_fork = nullptr, g_join = nullptr;
+// side stream + fork/join events, one set per (host thread, device)
+#define MAX_DEVICES 64
+struct Side {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+static thread_local Side g_sides[MAX_DEVICES];
 
-static int side_init() {
-    if (g_side) return 0;
-    CU_TRY(cudaStreamCreateWithFlags(&g_side, cudaStreamNonBlocking));
-    CU_TRY(cudaEventCreateWithFlags(&g_fork, cudaEventDisableTiming));
-    CU_TRY(cudaEventCreateWithFlags(&g_join, cudaEventDisableTiming));
+static int side_get(Side** out) {
+    int dev = 0;
+    CU_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= MAX_DEVICES) return fail(CLOOPS_EINVAL, "device ordinal %d out of range", dev);
+    Side& s = g_sides[dev];
+    if (!s.stream) {
+        CU_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        CU_TRY(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming));
+    }
+    *out = &s;
     return 0;
 }
 
@@ -96,12 +107,13 @@ static int pass_run(cloops_pass* p, const int32_t* d_x, const int32_t* d_y, int6
     if (n == 0) return 0;
     RET_IF(pool_init());
     cloops_coverage* cov = nullptr;
+    Side* side = nullptr;
     if (score) {                                   // fork: coverage sorts on the side stream
-        RET_IF(side_init());
-        CU_TRY(cudaEventRecord(g_fork, st));
-        CU_TRY(cudaStreamWaitEvent(g_side, g_fork, 0));
-        RET_IF(coverage_build(d_x, d_y, n, &cov, g_side));
-        CU_TRY(cudaEventRecord(g_join, g_side));
+        RET_IF(side_get(&side));
+        CU_TRY(cudaEventRecord(side->fork, st));
+        CU_TRY(cudaStreamWaitEvent(side->stream, side->fork, 0));
+        RET_IF(coverage_build(d_x, d_y, n, &cov, side->stream));
+        CU_TRY(cudaEventRecord(side->join, side->stream));
     }
     int rc = 0;
     cloops_index* ix = nullptr;
@@ -143,7 +155,7 @@ static int pass_run(cloops_pass* p, const int32_t* d_x, const int32_t* d_y, int6
             cub::DeviceScan::ExclusiveSum(d_scan, bytes, flag, pos, k, st);
             cand_scatter_kernel<<<cdiv(k, 256), 256, 0, st>>>(p->kind, pos, p->bbox, k, p->cand, p->d_m);
             g_launches.fetch_add(1);
-            CU_TRY(cudaStreamWaitEvent(st, g_join, 0));          // join: coverage model ready
+            CU_TRY(cudaStreamWaitEvent(st, side->join, 0));      // join: coverage model ready
             if ((rc = range_counts_dev(cov, p->cand, k, p->d_m, p->counts, st))) break;
             CU_TRY(cudaMemcpyAsync(&p->m, p->d_m, sizeof(int), cudaMemcpyDeviceToHost, st));
             CU_TRY(cudaStreamSynchronize(st));
@@ -152,7 +164,7 @@ static int pass_run(cloops_pass* p, const int32_t* d_x, const int32_t* d_y, int6
         }
     } while (0);
     if (score) {
-        cudaStreamWaitEvent(st, g_join, 0);                       // never free the model while the side stream builds it
+        cudaStreamWaitEvent(st, side->join, 0);                   // never free the model while the side stream builds it
         cloops_coverage_release(cov, st);
         if (rc == 0) p->scored = 1;
     }
