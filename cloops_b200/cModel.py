@@ -203,12 +203,19 @@ def removeDup(ds, bpcut=1e-5):
         order = np.argsort(a0, kind="stable")
         a0s = a0[order]
         wmax = int((a1 - a0).max())
+    if proper:
+        # loops whose left anchor cannot intersect any other left anchor are unique without any test
+        los = np.searchsorted(a0s, a0 - wmax, side="left")
+        his = np.searchsorted(a0s, a1, side="right")
+        lonely = (his - los) <= 1
     for i in range(n - 1):
         if taken[i]:
             continue
         if proper:
-            lo = np.searchsorted(a0s, a0[i] - wmax, side="left")
-            hi = np.searchsorted(a0s, a1[i], side="right")
+            if lonely[i]:
+                uniqueds[keys[i]] = ds[keys[i]]
+                continue
+            lo, hi = los[i], his[i]
             j = order[lo:hi]
             j = np.sort(j[(j > i)])
             j = j[~taken[j]]
