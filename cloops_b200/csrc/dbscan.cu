@@ -52,6 +52,22 @@ __device__ __forceinline__ void block_count(int* slots, bool pred) {
     if (threadIdx.x == 0 && total) atomicAdd(&slots[(blockIdx.x % CTR_SLOTS) * CTR_STRIDE], total);
 }
 
+// CTA-level compaction: the threads whose predicate holds are queued (by local thread id) so that the
+// first *s_n threads of the CTA continue with dense warps.  Kernels that only work on core points (or
+// only on non-core points) otherwise run with a third of their lanes active.
+__device__ __forceinline__ int cta_compact(bool pred, int* q, int* s_n) {
+    if (threadIdx.x == 0) *s_n = 0;
+    __syncthreads();
+    const unsigned b = __ballot_sync(0xffffffffu, pred);
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0 && b) base = atomicAdd(s_n, __popc(b));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (pred) q[base + __popc(b & ((1u << lane) - 1))] = threadIdx.x;
+    __syncthreads();
+    return *s_n;
+}
+
 __global__ void __launch_bounds__(256) fill_int_kernel(int* p, int v, long long n) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
@@ -155,10 +171,15 @@ __global__ void __launch_bounds__(256) clamp_next_head_kernel(int* __restrict__ 
 __global__ void __launch_bounds__(256) union_kernel(const u64* __restrict__ keys, const int* __restrict__ sstart, GridParams P,
                                                     const int* __restrict__ chain, const int* __restrict__ next_head,
                                                     int* __restrict__ seen, int* __restrict__ parent) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.n_act) return;
+    __shared__ int q[256];
+    __shared__ int s_n;
+    {
+        const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
+        const bool core = i0 < P.n_act && (keys[i0] >> 63);
+        if ((int)threadIdx.x >= cta_compact(core, q, &s_n)) return;
+    }
+    const int i = blockIdx.x * blockDim.x + q[threadIdx.x];
     const u64 key = keys[i];
-    if (!(key >> 63)) return;
     const PointView p = view(key, P);
     const int lo_s = __ldg(sstart + p.s + 1);
     const int a = __ldg(sstart + p.s);
@@ -239,10 +260,15 @@ __device__ __forceinline__ int root_of(const int* parent, int x) {
 // ---- v1 border ownership --------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) v1_border_kernel(const u64* __restrict__ keys, const int* __restrict__ sstart,
                                                         const u32* __restrict__ rows, GridParams P, Work W) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.n_act) return;
+    __shared__ int q[256];
+    __shared__ int s_n;
+    {
+        const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
+        const bool todo = i0 < P.n_act && !(keys[i0] >> 63);
+        if ((int)threadIdx.x >= cta_compact(todo, q, &s_n)) return;
+    }
+    const int i = blockIdx.x * blockDim.x + q[threadIdx.x];
     const u64 key = keys[i];
-    if (key >> 63) return;
     const PointView p = view(key, P);
     int best_seed_rank = -1, best_seed_root = -1, best_any_rank = INT_MAX, best_any_root = -1;
     for_each_neighbour(keys, sstart, P, i, p, [&](int j, u64 kq) {
@@ -341,11 +367,20 @@ __global__ void __launch_bounds__(256) v2_decide_kernel(Work W, int n_und, int m
 template <bool FIX>
 __global__ void __launch_bounds__(256) v2_border_kernel(const u64* __restrict__ keys, const int* __restrict__ sstart,
                                                         GridParams P, Work W, int n_items) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_items) return;
-    const int i = FIX ? W.list_con[t] : t;
+    __shared__ int q[256];
+    __shared__ int s_n;
+    int i;
+    if (FIX) {
+        const int t = blockIdx.x * blockDim.x + threadIdx.x;
+        if (t >= n_items) return;
+        i = W.list_con[t];
+    } else {                                             // every non-core point, compacted into dense warps
+        const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
+        const bool todo = i0 < n_items && !(keys[i0] >> 63);
+        if ((int)threadIdx.x >= cta_compact(todo, q, &s_n)) return;
+        i = blockIdx.x * blockDim.x + q[threadIdx.x];
+    }
     const u64 key = keys[i];
-    if (!FIX && (key >> 63)) return;
     const PointView p = view(key, P);
     int best_rank = INT_MAX, best_root = -1;
     bool contested = false;
