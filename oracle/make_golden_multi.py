@@ -71,5 +71,30 @@ def main():
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+def main_auto_eps():
+    """tests/golden/multi_auto_eps.loop: the same input through pipe(fs, out, eps=0, minPts=[6], hic=0),
+    i.e. the reference's auto-eps path (parseRawBedpe + estFragSize, cLoops/pipe.py:229-239)."""
+    ns = ref_shim.load()
+    logging.disable(logging.CRITICAL)
+    ns.pipe.logger = logging.getLogger("ref")
+    tmp = tempfile.mkdtemp(prefix="cloops_gold3_")
+    cwd = os.getcwd()
+    os.chdir(tmp)
+    try:
+        write_bedpe("in.bedpe", inputs())
+        so, se = sys.stdout, sys.stderr
+        sys.stdout, sys.stderr = io.StringIO(), io.StringIO()
+        try:
+            ns.pipe.pipe(["in.bedpe"], "gold", 0, [6], cpu=1, tmp=0, hic=0)
+        finally:
+            sys.stdout, sys.stderr = so, se
+        shutil.copy("gold.loop", os.path.join(GOLD, "multi_auto_eps.loop"))
+        print("auto-eps loop lines:", sum(1 for _ in open("gold.loop")))
+    finally:
+        os.chdir(cwd)
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 if __name__ == "__main__":
     main()
+    main_auto_eps()

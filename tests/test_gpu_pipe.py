@@ -127,3 +127,17 @@ def test_cli_main(need_gpu, gold_dir, tmp_path, monkeypatch):
     assert os.path.isdir(tmp_path / "b")
     pipe.main(["-f", bedpe, "-o", "b", "-m", "1"])           # existing output directory: refuse, leave results alone
     assert open(tmp_path / "b.loop", "rb").read() == want
+
+
+def test_pipe_auto_eps(need_gpu, gold_dir, tmp_path, monkeypatch):
+    """eps = 0: duplicate-dropping ingest + estFragSize (cLoops/pipe.py:229-239, io.py:62-129)."""
+    from cloops_b200 import pipe
+    gold = np.load(os.path.join(gold_dir, "multi_hic.npz"))
+    bedpe = str(tmp_path / "in.bedpe")
+    with open(bedpe, "w") as fh:
+        for name in ("chr1", "chr2", "chrX"):
+            for x, y in zip(gold[name + "_X"].tolist(), gold[name + "_Y"].tolist()):
+                fh.write("%s\t%d\t%d\t%s\t%d\t%d\tp\t.\t+\t-\n" % (name, x, x, name, y, y))
+    monkeypatch.chdir(tmp_path)
+    pipe.pipe([bedpe], "out", 0, [6], cpu=1, tmp=0, hic=0)
+    assert open(tmp_path / "out.loop", "rb").read() == open(os.path.join(gold_dir, "multi_auto_eps.loop"), "rb").read()
