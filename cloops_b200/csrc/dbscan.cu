@@ -257,6 +257,24 @@ __device__ __forceinline__ int root_of(const int* parent, int x) {
     return x;
 }
 
+// Neighbours of one point mostly belong to one component (after compress_kernel their parent IS the
+// root), so the (root, rank, status) triple of the previous neighbour is reused when the parent repeats:
+// one coalesced-ish load instead of three dependent random ones per core neighbour.
+struct RootCache {
+    int last_parent = -1, root = -1, rank = INT_MAX;
+    unsigned char status = ST_NONE;
+    __device__ __forceinline__ void lookup(const Work& W, int j) {
+        const int pj = W.parent[j];
+        if (pj == last_parent) return;
+        last_parent = pj;
+        int x = pj, q = W.parent[x];
+        while (q != x) { x = q; q = W.parent[x]; }
+        root = x;
+        rank = W.rank[x];
+        status = W.status[x];
+    }
+};
+
 // ---- v1 border ownership --------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) v1_border_kernel(const u64* __restrict__ keys, const int* __restrict__ sstart,
                                                         const u32* __restrict__ rows, GridParams P, Work W) {
@@ -271,11 +289,12 @@ __global__ void __launch_bounds__(256) v1_border_kernel(const u64* __restrict__ 
     const u64 key = keys[i];
     const PointView p = view(key, P);
     int best_seed_rank = -1, best_seed_root = -1, best_any_rank = INT_MAX, best_any_root = -1;
+    RootCache rc;
     for_each_neighbour(keys, sstart, P, i, p, [&](int j, u64 kq) {
         if (!(kq >> 63)) return true;
-        int r = root_of(W.parent, j);
-        int rk = W.rank[r];
-        if ((int)rows[j] == rk && rk > best_seed_rank) { best_seed_rank = rk; best_seed_root = r; }
+        rc.lookup(W, j);
+        const int r = rc.root, rk = rc.rank;
+        if (rk > best_seed_rank && (int)rows[j] == rk) { best_seed_rank = rk; best_seed_root = r; }
         if (rk < best_any_rank) { best_any_rank = rk; best_any_root = r; }
         return true;
     });
@@ -323,12 +342,13 @@ __global__ void __launch_bounds__(128) v2_accumulate_kernel(const u64* __restric
     const int i = W.list_con[t];
     const PointView p = view(keys[i], P);
     int min_nd_rank = INT_MAX, min_nd_root = -1, min_alive_rank = INT_MAX;
+    RootCache rc;
     for_each_neighbour(keys, sstart, P, i, p, [&](int j, u64 kq) {
         if (!(kq >> 63)) return true;
-        int r = root_of(W.parent, j);
-        unsigned char st = W.status[r];
+        rc.lookup(W, j);
+        const int r = rc.root, rk = rc.rank;
+        const unsigned char st = rc.status;
         if (st == ST_DEAD) return true;
-        int rk = W.rank[r];
         if (rk < min_nd_rank) { min_nd_rank = rk; min_nd_root = r; }
         if (st == ST_ALIVE && rk < min_alive_rank) min_alive_rank = rk;
         return true;
@@ -336,10 +356,12 @@ __global__ void __launch_bounds__(128) v2_accumulate_kernel(const u64* __restric
     if (min_nd_root < 0) return;
     if (W.status[min_nd_root] == ST_UNDECIDED) atomicAdd(&W.size[min_nd_root], 1);
     // every distinct undecided adjacent component ranked below the best alive one
+    RootCache rc2;
     for_each_neighbour(keys, sstart, P, i, p, [&](int j, u64 kq) {
         if (!(kq >> 63)) return true;
-        int r = root_of(W.parent, j);
-        if (W.status[r] != ST_UNDECIDED || W.rank[r] >= min_alive_rank) return true;
+        rc2.lookup(W, j);
+        const int r = rc2.root;
+        if (rc2.status != ST_UNDECIDED || rc2.rank >= min_alive_rank) return true;
         bool first = true;                      // count each component once: only at its first visit
         for_each_neighbour(keys, sstart, P, i, p, [&](int j2, u64 kq2) {
             if (j2 == j) return false;
@@ -384,14 +406,13 @@ __global__ void __launch_bounds__(256) v2_border_kernel(const u64* __restrict__ 
     const PointView p = view(key, P);
     int best_rank = INT_MAX, best_root = -1;
     bool contested = false;
+    RootCache rc;
     for_each_neighbour(keys, sstart, P, i, p, [&](int j, u64 kq) {
         if (!(kq >> 63)) return true;
-        int r = root_of(W.parent, j);
-        unsigned char st = W.status[r];
-        if (st == ST_DEAD) return true;
-        if (st == ST_UNDECIDED) contested = true;
-        int rk = W.rank[r];
-        if (rk < best_rank) { best_rank = rk; best_root = r; }
+        rc.lookup(W, j);
+        if (rc.status == ST_DEAD) return true;
+        if (rc.status == ST_UNDECIDED) contested = true;
+        if (rc.rank < best_rank) { best_rank = rc.rank; best_root = rc.root; }
         return true;
     });
     W.assigned[i] = best_root;
