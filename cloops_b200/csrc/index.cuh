@@ -7,6 +7,7 @@ struct cloops_index {
     u64* keys = nullptr;      // [n] sorted packed keys (active rows first, inactive rows in sentinel strip)
     u32* rows = nullptr;      // [n] original row of each sorted position
     int* sstart = nullptr;    // [ns+3] dense strip offsets, entry k = first sorted index of strip k-1
+    void* tiles = nullptr;    // [ceil(n_act/1024)] per-tile headers of the region query (index.cu:TileInfo)
     int counted_cap = 0;      // cap of the counts currently flagged into the keys (0 = none)
 };
 
