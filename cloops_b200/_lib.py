@@ -25,7 +25,6 @@ _SIGNATURES = {
     "cloops_version": (C.c_char_p, []),
     "cloops_kernel_launches": (_i64, []),
     "cloops_set_profiling": (None, [C.c_int]),
-    "cloops_set_tuning": (None, [C.c_int, C.c_int]),
     "cloops_stage_count": (C.c_int, []),
     "cloops_stage_name": (C.c_char_p, [C.c_int]),
     "cloops_stage_ms": (C.c_float, [C.c_int]),

@@ -90,18 +90,8 @@ __global__ void __launch_bounds__(256) strip_table_search_kernel(const u64* __re
 
 // --------------------------------------------------------------------------------------------------
 // Region query: neighbour count per point, saturating at cap (cDBSCAN.py:186-205; cDBSCAN2.py:304-346).
-//
-// A CTA owns TILE consecutive sorted points.  Everything its threads can touch -- the strips of the
-// tile plus one strip below and one above -- is ONE contiguous key range R (strips are consecutive in
-// the sort order), staged once into shared memory as 32-bit u' and vmod arrays with coalesced loads.
-// Phase 1 (every thread): walk left/right inside the own strip; dense points saturate here.
-// Phase 2 (compacted): the still unsaturated points are queued in shared memory so that full warps run
-// the two binary searches + window scans of strips s-1 and s+1.
-// If R does not fit (very long strips: dense Hi-C diagonals, where phase 1 saturates almost at once)
-// the CTA falls back to the same walk on global memory through L1.
-#define CQ_TILE 256
-#define CQ_RMAX 2048
-
+// count_point_global is the per-point walk on global memory (through L1) that tiles with very long strips
+// fall back to; the production kernel is count_kernel_tiled below.
 __device__ __forceinline__ int count_point_global(const u64* __restrict__ keys, const int* __restrict__ sstart, const GridParams& P,
                                                   int cap, int i) {
     const PointView p = view(keys[i], P);
@@ -144,135 +134,6 @@ __device__ __forceinline__ int count_point_global(const u64* __restrict__ keys, 
     return c;
 }
 
-__device__ __forceinline__ int lower_bound_s(const u32* __restrict__ U, int lo, int hi, u32 target) {   // first U >= target
-    while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        if (U[mid] < target) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
-__device__ __forceinline__ int upper_bound_s(const u32* __restrict__ U, int lo, int hi, u32 target) {   // first U > target
-    while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        if (U[mid] <= target) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
-
-// window of an adjacent strip [a,b): 4 predicated probes from the lower bound (no divergence), then a
-// tail loop for the rare longer windows.  UPPER: strip s-1 needs vmod_q >= vmod_p, strip s+1 vmod_q <= vmod_p.
-template <bool PREV>
-__device__ __forceinline__ int adjacent_strip_count(const u32* __restrict__ U, const u32* __restrict__ V, int a, int b, int me,
-                                                    u32 ulo, u32 uhi, u32 vm, int c, int cap) {
-    int j = lower_bound_s(U, a, b, ulo);
-    bool in = true;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int jj = j + k;
-        in = in && jj < b;
-        const int js = in ? jj : me;
-        in = in && U[js] <= uhi;
-        const u32 vq = V[js];
-        c += (in && (PREV ? vq >= vm : vq <= vm)) ? 1 : 0;
-    }
-    if (in) {
-        for (int jj = j + 4; jj < b && c < cap; ++jj) {
-            if (U[jj] > uhi) break;
-            const u32 vq = V[jj];
-            c += (PREV ? vq >= vm : vq <= vm) ? 1 : 0;
-        }
-    }
-    return c;
-}
-
-__global__ void __launch_bounds__(CQ_TILE) count_kernel(const u64* __restrict__ keys, const int* __restrict__ sstart, GridParams P,
-                                                        int cap, int* __restrict__ cnt) {
-    __shared__ u32 U[CQ_RMAX];
-    __shared__ u32 V[CQ_RMAX];
-    __shared__ int q_pt[CQ_TILE];       // queued points (index relative to R)
-    __shared__ int q_c[CQ_TILE];        // their partial counts
-    __shared__ int q_s[CQ_TILE];        // their strips
-    __shared__ int s_sA, s_sB, s_nq;
-    const int tid = threadIdx.x;
-    const int t0 = blockIdx.x * CQ_TILE;
-    const int t1 = min(t0 + CQ_TILE, P.n_act);
-    const int i = t0 + tid;
-    int s = 0;
-    if (i < t1) {
-        s = (int)((__ldg(keys + i) & KEY_MASK) >> P.sshift);
-        if (tid == 0) { s_sA = s; s_nq = 0; }
-        if (i == t1 - 1) s_sB = s;
-    }
-    __syncthreads();
-    const int r0 = __ldg(sstart + s_sA);          // first point of strip sA-1
-    const int r1 = __ldg(sstart + s_sB + 3);      // end of strip sB+1
-    if (r1 - r0 > CQ_RMAX) {                      // CTA-uniform
-        if (i < t1) cnt[i] = count_point_global(keys, sstart, P, cap, i);
-        return;
-    }
-    for (int j = r0 + tid; j < r1; j += CQ_TILE) {
-        const u64 k = __ldg(keys + j);
-        U[j - r0] = (u32)(k >> P.be) & P.umask;
-        V[j - r0] = (u32)k & P.emask;
-    }
-    __syncthreads();
-    // ---- phase 1: own strip.  Uniform trip counts: the in-window predicate is monotone along the sorted
-    // strip, so probing the cap-1 nearest points on each side gives min(count, cap-1) per side.
-    int c = 1;
-    bool need = false;
-    const int me = i - r0;
-    if (i < t1) {
-        const int lo_s = __ldg(sstart + s + 1) - r0, hi_s = __ldg(sstart + s + 2) - r0;
-        const u32 up = U[me];
-        const u32 ulo = up > (u32)P.eps ? up - (u32)P.eps : 0u;
-        const u64 h = (u64)up + (u64)P.eps;
-        const u32 uhi = h < (u64)P.umask ? (u32)h : P.umask;
-        if (cap <= 9) {
-            for (int k = 1; k < cap; ++k) {
-                const int jl = me - k, jr = me + k;
-                const bool okl = jl >= lo_s, okr = jr < hi_s;
-                const u32 ul = U[okl ? jl : me], ur = U[okr ? jr : me];
-                c += (okl && ul >= ulo) ? 1 : 0;
-                c += (okr && ur <= uhi) ? 1 : 0;
-            }
-        } else {
-            c = upper_bound_s(U, me + 1, hi_s, uhi) - lower_bound_s(U, lo_s, me, ulo);
-        }
-        need = c < cap;
-        if (!need) cnt[i] = cap;
-    }
-    // ---- compaction of the unsaturated points
-    {
-        const unsigned b = __ballot_sync(0xffffffffu, need);
-        const int lane = tid & 31;
-        int base = 0;
-        if (lane == 0 && b) base = atomicAdd(&s_nq, __popc(b));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (need) {
-            const int slot = base + __popc(b & ((1u << lane) - 1));
-            q_pt[slot] = me;
-            q_c[slot] = c;
-            q_s[slot] = s;
-        }
-    }
-    __syncthreads();
-    // ---- phase 2: strips s-1 and s+1
-    if (tid < s_nq) {
-        const int pm = q_pt[tid];
-        const int ps = q_s[tid];
-        c = q_c[tid];
-        const u32 up = U[pm], vm = V[pm];
-        const u32 ulo = up > (u32)P.eps ? up - (u32)P.eps : 0u;
-        const u64 h = (u64)up + (u64)P.eps;
-        const u32 uhi = h < (u64)P.umask ? (u32)h : P.umask;
-        const int a = __ldg(sstart + ps) - r0, lo_s = __ldg(sstart + ps + 1) - r0;
-        const int hi_s = __ldg(sstart + ps + 2) - r0, b = __ldg(sstart + ps + 3) - r0;
-        c = adjacent_strip_count<true>(U, V, a, lo_s, pm, ulo, uhi, vm, c, cap);
-        if (c < cap) c = adjacent_strip_count<false>(U, V, hi_s, b, pm, ulo, uhi, vm, c, cap);
-        cnt[r0 + pm] = c < cap ? c : cap;
-    }
-}
-
 // --------------------------------------------------------------------------------------------------
 // Region query, tiled form (the production kernel).
 //
@@ -297,10 +158,10 @@ __global__ void __launch_bounds__(CQ_TILE) count_kernel(const u64* __restrict__ 
 // saturates at once) fall back to count_point_global.
 #define CT_THREADS 256
 #define CT_TILE 1024
-#define CT_RMAX 2560       // staged points per tile: 8 CTAs of 27 KB per SM
+#define CT_RMAX 2560       // staged points per tile: 8 CTAs of 27 KB per SM.  (Measured: a 4864-point variant at 4 CTAs/SM
+                           // is slower on long Hi-C strips than letting those tiles take the global fallback.)
 #define CT_G 8             // left guard words; the right side keeps 12
 #define CT_SMAX 1024
-#define CT_SLOTS (CT_RMAX + CT_G + 12 + 4)
 
 // c += (a >= b), c += (a <= b): compare + predicated add (the compiler's select form costs a third instruction)
 __device__ __forceinline__ void inc_ge(int& c, u32 a, u32 b) {
@@ -335,7 +196,7 @@ struct TileInfo {
 };
 
 __global__ void __launch_bounds__(128) tile_info_kernel(const u64* __restrict__ keys, const int* __restrict__ sstart, GridParams P,
-                                                        int ntiles, TileInfo* __restrict__ tiles) {
+                                                        int ntiles, int rmax, TileInfo* __restrict__ tiles) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= ntiles) return;
     const int t0 = b * CT_TILE, t1 = min(t0 + CT_TILE, P.n_act);
@@ -346,7 +207,7 @@ __global__ void __launch_bounds__(128) tile_info_kernel(const u64* __restrict__ 
     ti.r0 = sstart[ti.sA];
     ti.r1 = sstart[sB + 3];
     ti.meta = 0;
-    if (ti.r1 - ti.r0 <= CT_RMAX && nse <= CT_SMAX && ((u64)nse << P.bu) <= 0xffffffffull) {
+    if (ti.r1 - ti.r0 <= rmax && nse <= CT_SMAX && ((u64)nse << P.bu) <= 0xffffffffull) {
         int maxlen = 0, prev = ti.r0;
         for (int k = 1; k < nse; ++k) {
             const int cur = sstart[ti.sA + k];
@@ -381,38 +242,41 @@ __device__ __forceinline__ u32 uniform_lower_bound(u32 pa, u32 t, int nsteps, u3
 template <bool NEXT>
 __device__ __forceinline__ int adjacent_count(u32 sa, u32 dv, u32 tlo, u32 thi, u32 vm, int nsteps, u32 last_a, int room) {
     const u32 ja = uniform_lower_bound(sa, tlo, nsteps, last_a);
-    const u32 va = ja + dv;
+    const u32 w0 = lds_off<0>(ja);
     int f = 0;
-    const u32 w3 = lds_off<12>(ja);
-    if (NEXT) {
-        inc_in_window_le(f, lds_off<0>(ja), thi, lds_off<0>(va), vm);
-        inc_in_window_le(f, lds_off<4>(ja), thi, lds_off<4>(va), vm);
-        inc_in_window_le(f, lds_off<8>(ja), thi, lds_off<8>(va), vm);
-        inc_in_window_le(f, w3, thi, lds_off<12>(va), vm);
-    } else {
-        inc_in_window_ge(f, lds_off<0>(ja), thi, lds_off<0>(va), vm);
-        inc_in_window_ge(f, lds_off<4>(ja), thi, lds_off<4>(va), vm);
-        inc_in_window_ge(f, lds_off<8>(ja), thi, lds_off<8>(va), vm);
-        inc_in_window_ge(f, w3, thi, lds_off<12>(va), vm);
-    }
-    if (w3 <= thi) {                                                       // rare: more than four points in the window
-        for (u32 a = ja + 16u; f < room && lds_off<0>(a) <= thi; a += 4u) {
-            const u32 v = lds_off<0>(a + dv);
-            f += (NEXT ? v <= vm : v >= vm) ? 1 : 0;
+    if (w0 <= thi) {                               // most windows are empty: their lanes issue no further loads
+        const u32 va = ja + dv;
+        const u32 w3 = lds_off<12>(ja);
+        if (NEXT) {
+            f = lds_off<0>(va) <= vm ? 1 : 0;
+            inc_in_window_le(f, lds_off<4>(ja), thi, lds_off<4>(va), vm);
+            inc_in_window_le(f, lds_off<8>(ja), thi, lds_off<8>(va), vm);
+            inc_in_window_le(f, w3, thi, lds_off<12>(va), vm);
+        } else {
+            f = lds_off<0>(va) >= vm ? 1 : 0;
+            inc_in_window_ge(f, lds_off<4>(ja), thi, lds_off<4>(va), vm);
+            inc_in_window_ge(f, lds_off<8>(ja), thi, lds_off<8>(va), vm);
+            inc_in_window_ge(f, w3, thi, lds_off<12>(va), vm);
+        }
+        if (w3 <= thi) {                                                   // rare: more than four points in the window
+            for (u32 a = ja + 16u; f < room && lds_off<0>(a) <= thi; a += 4u) {
+                const u32 v = lds_off<0>(a + dv);
+                f += (NEXT ? v <= vm : v >= vm) ? 1 : 0;
+            }
         }
     }
     return f;
 }
 
-template <int CAPT>
+template <int CAPT, int RMAX>
 __global__ void __launch_bounds__(CT_THREADS) count_kernel_tiled(const u64* __restrict__ keys, const int* __restrict__ sstart,
                                                                   const TileInfo* __restrict__ tiles, GridParams P, int cap_rt,
                                                                   int* __restrict__ cnt, int vec_ok) {
     constexpr int NV = CAPT == 0 ? 0 : (CAPT > 5 ? 2 : 1);              // 128-bit words of context on each side
     constexpr int NP = CAPT > 0 ? CAPT - 1 : 0;                          // probes on each side
     typedef typename std::conditional<(CAPT > 0), unsigned short, u32>::type QT;   // queue entry: point | count << 10
-    __shared__ __align__(16) u32 Wg[CT_SLOTS];
-    __shared__ __align__(16) u32 Vg[CT_SLOTS];
+    __shared__ __align__(16) u32 Wg[RMAX + CT_G + 12 + 4];
+    __shared__ __align__(16) u32 Vg[RMAX + CT_G + 12 + 4];
     __shared__ QT Q1[CT_TILE];
     __shared__ int S[CT_SMAX];
     __shared__ int s_nq1;
@@ -554,21 +418,21 @@ __global__ void __launch_bounds__(CT_THREADS) count_kernel_tiled(const u64* __re
     }
 }
 
+template <int RMAX>
 static int launch_count_tiled(const cloops_index* ix, int cap, int* out, cudaStream_t st) {
     const GridParams& P = ix->P;
     const int grid = cdiv(P.n_act, CT_TILE);
     const int vec_ok = (((uintptr_t)out) & 15) == 0 ? 1 : 0;
     const TileInfo* tiles = reinterpret_cast<const TileInfo*>(ix->tiles);
     switch (cap) {
-#define CT_CASE(C) case C: LAUNCH((count_kernel_tiled<C>), grid, CT_THREADS, 0, st, ix->keys, ix->sstart, tiles, P, cap, out, vec_ok); break;
+#define CT_CASE(C) case C: LAUNCH((count_kernel_tiled<C, RMAX>), grid, CT_THREADS, 0, st, ix->keys, ix->sstart, tiles, P, cap, out, vec_ok); break;
         CT_CASE(2) CT_CASE(3) CT_CASE(4) CT_CASE(5) CT_CASE(6) CT_CASE(7) CT_CASE(8) CT_CASE(9)
 #undef CT_CASE
-        default: LAUNCH((count_kernel_tiled<0>), grid, CT_THREADS, 0, st, ix->keys, ix->sstart, tiles, P, cap, out, vec_ok); break;
+        default: LAUNCH((count_kernel_tiled<0, RMAX>), grid, CT_THREADS, 0, st, ix->keys, ix->sstart, tiles, P, cap, out, vec_ok); break;
     }
     return 0;
 }
 
-int g_count_variant = 0;      // cloops_set_tuning(0, v): 0 = tiled kernel, 2 = round-1 kernel
 
 // (X, Y) of every active PET in index order, decoded from the packed keys
 __global__ void __launch_bounds__(256) coords_kernel(const u64* __restrict__ keys, GridParams P, int* __restrict__ xs, int* __restrict__ ys) {
@@ -678,7 +542,8 @@ int index_build(const int32_t* d_x, const int32_t* d_y, int64_t n, int32_t eps, 
     {
         const int ntiles = cdiv(P.n_act, CT_TILE);
         CU_TRY(cudaMallocAsync((void**)&ix->tiles, (size_t)ntiles * sizeof(TileInfo), st));
-        LAUNCH(tile_info_kernel, cdiv(ntiles, 128), 128, 0, st, ix->keys, ix->sstart, P, ntiles, reinterpret_cast<TileInfo*>(ix->tiles));
+        ix->rmax = CT_RMAX;
+        LAUNCH(tile_info_kernel, cdiv(ntiles, 128), 128, 0, st, ix->keys, ix->sstart, P, ntiles, ix->rmax, reinterpret_cast<TileInfo*>(ix->tiles));
     }
     stage_mark("strips", st);
     return 0;
@@ -697,11 +562,7 @@ int index_count(cloops_index* ix, int cap, int* d_counts_sorted, cudaStream_t st
     const GridParams& P = ix->P;
     if (P.n_act == 0) return 0;
     if (cap <= 0) cap = INT_MAX;
-    if (g_count_variant == 2) {
-        LAUNCH(count_kernel, cdiv(P.n_act, CQ_TILE), CQ_TILE, 0, st, ix->keys, ix->sstart, P, cap, d_counts_sorted);
-        return 0;
-    }
-    return launch_count_tiled(ix, cap, d_counts_sorted, st);
+    return launch_count_tiled<CT_RMAX>(ix, cap, d_counts_sorted, st);
 }
 
 }  // namespace cloops

@@ -8,6 +8,7 @@ struct cloops_index {
     u32* rows = nullptr;      // [n] original row of each sorted position
     int* sstart = nullptr;    // [ns+3] dense strip offsets, entry k = first sorted index of strip k-1
     void* tiles = nullptr;    // [ceil(n_act/1024)] per-tile headers of the region query (index.cu:TileInfo)
+    int rmax = 0;             // staging capacity the tile headers were computed for
     int counted_cap = 0;      // cap of the counts currently flagged into the keys (0 = none)
 };
 

@@ -9,7 +9,6 @@ namespace cloops {
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
 bool g_profiling = false;
-extern int g_count_variant;
 bool g_debug_sync = getenv("CLOOPS_DEBUG_SYNC") != nullptr && getenv("CLOOPS_DEBUG_SYNC")[0] == '1';
 thread_local std::vector<StageRec> g_stages;
 static thread_local std::vector<cudaEvent_t> g_event_cache;
@@ -80,9 +79,6 @@ const char* cloops_last_error(void) { return g_err.c_str(); }
 const char* cloops_version(void) { return "cloops_b200 0.1 (sm_100a)"; }
 int64_t cloops_kernel_launches(void) { return (int64_t)g_launches.load(); }
 void cloops_set_profiling(int on) { g_profiling = on != 0; }
-void cloops_set_tuning(int knob, int value) {
-    if (knob == 0) g_count_variant = value;
-}
 int cloops_stage_count(void) { return g_stages.empty() ? 0 : (int)g_stages.size() - 1; }
 const char* cloops_stage_name(int i) { return (i >= 0 && i + 1 < (int)g_stages.size()) ? g_stages[i + 1].name : ""; }
 float cloops_stage_ms(int i) { return (i >= 0 && i + 1 < (int)g_stages.size()) ? g_stages[i + 1].ms : 0.f; }

@@ -52,9 +52,6 @@ CLOOPS_API int64_t cloops_kernel_launches(void);
  * cloops_stage_count()/cloops_stage_name(i)/cloops_stage_ms(i) describe the stages of the LAST
  * call on this thread (the call synchronises the stream when profiling is on). */
 CLOOPS_API void cloops_set_profiling(int on);
-/* developer knobs for A/B measurements; results never depend on them.  knob 0 = region-query kernel
- * (0: W form + occupancy bitmap [default], 1: W form, 2: round-1 kernel) */
-CLOOPS_API void cloops_set_tuning(int knob, int value);
 CLOOPS_API int cloops_stage_count(void);
 CLOOPS_API const char* cloops_stage_name(int i);
 CLOOPS_API float cloops_stage_ms(int i);

@@ -1,14 +1,15 @@
-"""CPU model of the region-query kernel's "W form" (cloops_b200/csrc/index.cu:count_kernel_w), checked
-against the oracle's neighbour counts.  It restates, tile by tile, exactly the integer algebra the kernel
-relies on -- padded u', W = (relative strip << bu) | u', one-compare window tests, guard words, the
-staged strip table, the hashed 3-cell occupancy bitmap -- so the algebra is verified without a GPU.
-(The CUDA kernel itself is compared with the oracle in the -m gpu tests.)"""
+"""CPU model of the region-query kernel (cloops_b200/csrc/index.cu:count_kernel_tiled), checked against
+the oracle's neighbour counts.  It restates, tile by tile, exactly the integer algebra the kernel relies
+on -- padded u', W = (relative strip << bu) | u' with one-compare window tests, guard words instead of
+bounds tests, slots that keep the global index modulo 4, the per-tile header, the uniform (fixed trip
+count) binary search that may run past a strip's end, 4 probes + tail -- so that algebra is verified
+without a GPU.  (The CUDA kernel itself is compared with the oracle in the -m gpu tests.)"""
 import numpy as np
 import pytest
 
 from oracle import spec
 
-TILE, RMAX, G, SMAX, BMW = 256, 2048, 8, 512, 512
+G, GR, SMAX = 8, 12, 1024
 
 
 def _bits(v):
@@ -16,7 +17,7 @@ def _bits(v):
 
 
 def build_index(X, Y, eps):
-    """mirror of index_build(): padded u', packed (strip,u') word and vmod, sorted by (strip,u')"""
+    """mirror of index_build(): padded u', (strip,u') word and vmod, sorted by (strip,u'), dense strip table"""
     u = X - Y
     v = X + Y
     ubase = (u.min() // eps) * eps - eps
@@ -34,100 +35,102 @@ def build_index(X, Y, eps):
     return ks[order], vm[order], order, sstart, be, bu
 
 
-def lower_bound(W, lo, hi, t):
-    while lo < hi:
-        mid = (lo + hi) >> 1
-        if W[mid] < t:
-            lo = mid + 1
-        else:
-            hi = mid
-    return lo
+def tile_info(ks, sstart, bu, t0, t1, rmax):
+    """mirror of tile_info_kernel"""
+    sA, sB = int(ks[t0] >> bu), int(ks[t1 - 1] >> bu)
+    nse = sB - sA + 4
+    r0, r1 = int(sstart[sA]), int(sstart[sB + 3])
+    if r1 - r0 > rmax or nse > SMAX or (nse << bu) > 0xFFFFFFFF:
+        return sA, r0, r1, 0, 0
+    maxlen = int(np.diff(sstart[sA:sA + nse]).max())
+    return sA, r0, r1, nse, maxlen.bit_length()
 
 
-def upper_bound(W, lo, hi, t):
-    while lo < hi:
-        mid = (lo + hi) >> 1
-        if W[mid] <= t:
-            lo = mid + 1
-        else:
-            hi = mid
-    return lo
+def uniform_lower_bound(W, pa, t, nsteps, last):
+    """pa = slot of the largest word known to be < t; returns the first slot whose word is >= t"""
+    sb = 2 << nsteps                       # in words * 4 like the kernel's byte steps: compare against 32 bytes
+    while sb > 32:
+        na = min(pa + sb // 4, last)
+        if W[na] < t:
+            pa = na
+        sb >>= 1
+    for step in (8, 4, 2, 1):
+        if W[pa + step] < t:
+            pa += step
+    return pa + 1
 
 
-def model_counts(X, Y, eps, cap, bitmap=True, tile=TILE):
+def adjacent_count(W, V, sa, tlo, thi, vm, nsteps, last, room, nxt):
+    j = uniform_lower_bound(W, sa, tlo, nsteps, last)
+    f = 0
+    if W[j] <= thi:
+        for k in range(4):
+            f += int(W[j + k] <= thi and (V[j + k] <= vm if nxt else V[j + k] >= vm))
+        if W[j + 3] <= thi:
+            a = j + 4
+            while f < room and W[a] <= thi:
+                f += int(V[a] <= vm if nxt else V[a] >= vm)
+                a += 1
+    return f
+
+
+def model_counts(X, Y, eps, cap, tile=1024, rmax=2560):
     ks, vmod, order, sstart, be, bu = build_index(X, Y, eps)
     n = len(ks)
-    strip_of = ks >> bu
     out = np.zeros(n, dtype=np.int64)
     one = 1 << bu
-    M = BMW * 32
-    stats = {"fallback": 0, "pruned": 0, "searched": 0}
-
-    def h(w):
-        return ((w >> be) + (w >> bu) * 1237) & 0xFFFFFFFF
-
+    stats = {"fallback": 0, "tiles": 0, "queued": 0}
+    templated = 2 <= cap <= 9              # CAPT > 0: probing form
     for t0 in range(0, n, tile):
         t1 = min(t0 + tile, n)
-        sA, sB = int(strip_of[t0]), int(strip_of[t1 - 1])
-        nse = sB - sA + 4
-        r0, r1 = int(sstart[sA]), int(sstart[sB + 3])
-        ln = r1 - r0
-        if ln > RMAX or nse > SMAX or (nse << bu) > 0xFFFFFFFF:
+        sA, r0, r1, nse, nsteps = tile_info(ks, sstart, bu, t0, t1, rmax)
+        stats["tiles"] += 1
+        if nse == 0:
             stats["fallback"] += 1
             xs, ys = X[order], Y[order]
             for i in range(t0, t1):
-                d = np.abs(xs - xs[i]) + np.abs(ys - ys[i])
-                out[i] = min(int((d <= eps).sum()), cap)
+                out[i] = min(int((np.abs(xs - xs[i]) + np.abs(ys - ys[i]) <= eps).sum()), cap)
             continue
-        base = (sA - 1) << bu
-        W = np.empty(ln + 2 * G, dtype=np.int64)
-        V = np.zeros(ln + 2 * G, dtype=np.int64)
-        W[:G] = 0
-        W[G + ln:] = 0xFFFFFFFF
-        W[G:G + ln] = ks[r0:r1] - base
-        assert W[G:G + ln].min() >= 0 and W[G:G + ln].max() < 0xFFFFFFFF
-        V[G:G + ln] = vmod[r0:r1]
-        S = sstart[sA:sA + nse] - r0 + G
-        BM = np.zeros(M, dtype=bool)
-        BM[h(W[G:G + ln]) & (M - 1)] = True
+        sl0 = G - (r0 & ~3)                # slot of global index j = sl0 + j
+        size = sl0 + r1 + GR
+        W = np.full(size, -1, dtype=np.int64)      # -1 = never written: reading it is a model error
+        V = np.full(size, -1, dtype=np.int64)
+        W[sl0 + r0:sl0 + r1] = ks[r0:r1] - ((sA - 1) << bu)
+        V[sl0 + r0:sl0 + r1] = vmod[r0:r1]
+        assert W[sl0 + r0:sl0 + r1].min() >= 0 and W[sl0 + r0:sl0 + r1].max() < 0xFFFFFFFF
+        W[sl0 + r0 - G:sl0 + r0] = 0
+        V[sl0 + r0 - G:sl0 + r0] = 0
+        W[sl0 + r1:sl0 + r1 + GR] = 0xFFFFFFFF
+        V[sl0 + r1:sl0 + r1 + GR] = 0
+        assert sl0 + r0 - G >= 0
+        S = sstart[sA:sA + nse] + sl0
+        last = sl0 + r1
+        queue = []
         for i in range(t0, t1):
-            me = G + i - r0
+            me = sl0 + i
             wp = int(W[me])
             lo, hi = wp - eps, wp + eps
-            assert lo >= 0
-            if cap <= G + 1:
+            assert lo >= 0 and hi < 0xFFFFFFFF
+            if templated:
                 c = 1
-                for k in range(1, cap):
-                    c += int(W[me - k] >= lo) + int(W[me + k] <= hi)
+                for q in range(1, cap):
+                    assert W[me - q] >= 0 and W[me + q] >= 0          # probes stay inside data + guards
+                    c += int(W[me - q] >= lo) + int(W[me + q] <= hi)
+            elif cap > 1:
+                sa = int(S[wp >> bu]) - 1
+                c = uniform_lower_bound(W, sa, hi + 1, nsteps, last) - uniform_lower_bound(W, sa, lo, nsteps, last)
             else:
-                srel = wp >> bu
-                c = upper_bound(W, me + 1, int(S[srel + 1]), hi) - lower_bound(W, int(S[srel]), me, lo)
-            dirs = 3
-            if c < cap and bitmap:
-                dirs = 0
-                for bit, wq in ((1, wp - one), (2, wp + one)):
-                    h0 = (h(wq) - 1) & (M - 1)
-                    if BM[h0] or BM[(h0 + 1) & (M - 1)] or BM[(h0 + 2) & (M - 1)]:
-                        dirs |= bit
-                stats["pruned"] += 2 - bin(dirs).count("1")
-            if c < cap and dirs:
-                vm = int(V[me])
-                srel = wp >> bu
-                for bit, a, b, tlo, prev in ((1, S[srel - 1], S[srel], wp - one - eps, True),
-                                             (2, S[srel + 1], S[srel + 2], wp + one - eps, False)):
-                    if not (dirs & bit) or c >= cap:
-                        continue
-                    stats["searched"] += 1
-                    thi = tlo + 2 * eps
-                    assert tlo >= 0 and thi < 0xFFFFFFFF
-                    j = lower_bound(W, int(a), int(b), tlo)
-                    for k in range(4):
-                        c += int(W[j + k] <= thi and (V[j + k] >= vm if prev else V[j + k] <= vm))
-                    if W[j + 3] <= thi:
-                        jj = j + 4
-                        while c < cap and W[jj] <= thi:
-                            c += int(V[jj] >= vm if prev else V[jj] <= vm)
-                            jj += 1
+                c = 1
+            out[i] = min(c, cap)
+            if c < cap:
+                queue.append((i, me, c))
+        stats["queued"] += len(queue)
+        for i, me, c in queue:
+            wp, vm = int(W[me]), int(V[me])
+            srel = wp >> bu
+            c += adjacent_count(W, V, int(S[srel - 1]) - 1, wp - one - eps, wp - one + eps, vm, nsteps, last, cap - c, False)
+            if c < cap:
+                c += adjacent_count(W, V, int(S[srel + 1]) - 1, wp + one - eps, wp + one + eps, vm, nsteps, last, cap - c, True)
             out[i] = min(c, cap)
     res = np.empty(n, dtype=np.int64)
     res[order] = out
@@ -138,7 +141,7 @@ def _cases():
     rng = np.random.default_rng(11)
     # sparse background + dense clumps + duplicates + negative coordinates
     for n, span, eps in ((1500, 200_000, 1000), (1200, 30_000, 500), (900, 5_000_000, 1000), (700, 4000, 7), (600, 2000, 1),
-                         (3000, 60_000, 1024)):
+                         (3000, 60_000, 1024), (2500, 20_000, 3000)):
         X = rng.integers(0, span, n)
         d = np.exp(rng.uniform(np.log(10), np.log(max(20, span // 2)), n)).astype(np.int64)
         Y = X + d
@@ -155,17 +158,15 @@ def _cases():
         yield X.astype(np.int64), Y.astype(np.int64), eps
 
 
-@pytest.mark.parametrize("bitmap", [True, False])
-def test_w_form_model_matches_oracle(bitmap):
-    searched = pruned = 0
+@pytest.mark.parametrize("tile,rmax", [(1024, 2560), (256, 640), (64, 4864)])
+def test_tiled_region_query_model_matches_oracle(tile, rmax):
+    queued = tiles = fallback = 0
     for X, Y, eps in _cases():
         want = spec.neighbour_counts(X, Y, eps)
-        for cap in (2, 5, 9, 10, 40, 1 << 30):
-            for tile in (256, 64):
-                got, st = model_counts(X, Y, eps, cap, bitmap=bitmap, tile=tile)
-                assert np.array_equal(got, np.minimum(want, cap)), (eps, cap, tile, np.flatnonzero(got != np.minimum(want, cap))[:5])
-                searched += st["searched"]
-                pruned += st["pruned"]
-    assert searched > 0
-    if bitmap:
-        assert pruned > 0
+        for cap in (1, 2, 5, 9, 10, 40, 1 << 30):
+            got, st = model_counts(X, Y, eps, cap, tile=tile, rmax=rmax)
+            assert np.array_equal(got, np.minimum(want, cap)), (eps, cap, tile, np.flatnonzero(got != np.minimum(want, cap))[:5])
+            queued += st["queued"]
+            tiles += st["tiles"]
+            fallback += st["fallback"]
+    assert queued > 0 and fallback < tiles
