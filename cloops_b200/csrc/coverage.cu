@@ -1,7 +1,8 @@
 // Permuted-local-background range counting (cLoops/cModel.py:31-143).
 //
-// Coverage model (cModel.py:45-57): the chromosome's PETs sorted by X and, separately, by Y, so that
-// "X in [lo,hi]" and "Y in [lo,hi]" are contiguous slices (the reference's np.searchsorted, :65-66).
+// Coverage model (cModel.py:45-57): the chromosome's PETs sorted by X and, separately, by Y (down to 256-bp
+// buckets, see COV_COARSE), so that "X in [lo,hi]" and "Y in [lo,hi]" are contiguous slices (the reference's
+// np.searchsorted, :65-66).
 // For a candidate (iva, ivb) the kernel evaluates the reference's set algebra as per-PET bit masks:
 //   in(W,p) = X_p in W  or  Y_p in W   (union of source and target hits, :73-78,:118-127)
 //   ra = #in(A), rb = #in(B), rab = #{X in A and Y in B}  (:72-80)
@@ -81,14 +82,20 @@ __device__ void make_windows(int iva0, int iva1, int ivb0, int ivb1, int win, Wi
     else { W.nh = 2; W.h0[0] = ha0; W.h1[0] = ha1; W.h0[1] = hb0; W.h1[1] = hb1; }
 }
 
-__device__ __forceinline__ int lower_bound_i(const int* __restrict__ a, int n, int v) {   // first idx with a[idx] >= v
+// The sorted views are ordered by the coordinate's bits >= COV_COARSE only (one radix pass fewer): PETs inside one
+// 2^COV_COARSE-bp bucket are in arbitrary order.  Slices are therefore cut at bucket granularity -- a superset of
+// the exact slice by a few PETs on either side -- and the kernel tests every coordinate exactly.
+#define COV_COARSE 8
+__device__ __forceinline__ int lower_bound_i(const int* __restrict__ a, int n, int v) {   // first idx whose bucket >= bucket(v)
     int lo = 0, hi = n;
-    while (lo < hi) { int mid = (lo + hi) >> 1; if (__ldg(a + mid) < v) lo = mid + 1; else hi = mid; }
+    const int bv = v >> COV_COARSE;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if ((__ldg(a + mid) >> COV_COARSE) < bv) lo = mid + 1; else hi = mid; }
     return lo;
 }
-__device__ __forceinline__ int upper_bound_i(const int* __restrict__ a, int n, int v) {   // first idx with a[idx] > v
+__device__ __forceinline__ int upper_bound_i(const int* __restrict__ a, int n, int v) {   // first idx whose bucket > bucket(v)
     int lo = 0, hi = n;
-    while (lo < hi) { int mid = (lo + hi) >> 1; if (__ldg(a + mid) <= v) lo = mid + 1; else hi = mid; }
+    const int bv = v >> COV_COARSE;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if ((__ldg(a + mid) >> COV_COARSE) <= bv) lo = mid + 1; else hi = mid; }
     return lo;
 }
 
@@ -140,8 +147,8 @@ __global__ void __launch_bounds__(32 * RC_WARPS) range_count_kernel(const int* _
             if (via_y) {
                 bool seen = false;                             // already visited through its X
                 for (int g = 0; g < nh; ++g) seen |= (x >= W.h0[g] && x <= W.h1[g]);
-                if (seen) continue;
-            }
+                if (seen || y < W.h0[h] || y > W.h1[h]) continue;   // (the slice is cut at bucket granularity)
+            } else if (x < W.h0[h] || x > W.h1[h]) continue;
             // a coordinate can only fall into a window of a family whose hull contains it: the X-sorted
             // slice is inside one hull by construction, and the partner coordinate is usually far away
             unsigned ma = 0, mb = 0;
@@ -188,11 +195,11 @@ int coverage_build(const int32_t* d_x, const int32_t* d_y, int64_t n, cloops_cov
     CU_TRY(cudaMallocAsync((void**)&cov->ys_x, n * sizeof(int), st));
     Temp tmp(st);
     size_t bytes = 0;
-    CU_TRY(cub::DeviceRadixSort::SortPairs(nullptr, bytes, d_x, cov->xs_x, d_y, cov->xs_y, (int)n, 0, 32, st));
+    CU_TRY(cub::DeviceRadixSort::SortPairs(nullptr, bytes, d_x, cov->xs_x, d_y, cov->xs_y, (int)n, COV_COARSE, 32, st));
     void* d_tmp;
     RET_IF(tmp.alloc((char**)&d_tmp, bytes));
-    CU_TRY(cub::DeviceRadixSort::SortPairs(d_tmp, bytes, d_x, cov->xs_x, d_y, cov->xs_y, (int)n, 0, 32, st));
-    CU_TRY(cub::DeviceRadixSort::SortPairs(d_tmp, bytes, d_y, cov->ys_y, d_x, cov->ys_x, (int)n, 0, 32, st));
+    CU_TRY(cub::DeviceRadixSort::SortPairs(d_tmp, bytes, d_x, cov->xs_x, d_y, cov->xs_y, (int)n, COV_COARSE, 32, st));
+    CU_TRY(cub::DeviceRadixSort::SortPairs(d_tmp, bytes, d_y, cov->ys_y, d_x, cov->ys_x, (int)n, COV_COARSE, 32, st));
     return 0;
 }
 

@@ -50,34 +50,170 @@ __global__ void __launch_bounds__(256) extents_kernel(const int* __restrict__ x,
     }
 }
 
+// Packs the key of every row.  RANK: also counts the rows of each strip (cnt[strip + 1], the layout of the strip
+// table) and remembers each row's arrival rank inside its strip, so that one exclusive scan of cnt IS the strip
+// table and the rows can be placed next to their strip without a radix sort (index_build).  Rows removed by the
+// cut filter are ranked behind the active ones through cnt_tail.
+template <bool RANK>
 __global__ void __launch_bounds__(256) pack_kernel(const int* __restrict__ x, const int* __restrict__ y, int cut, GridParams P,
-                                                   u64* __restrict__ keys, u32* __restrict__ rows) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.n) return;
-    int xx = __ldg(x + i), yy = __ldg(y + i);
-    u64 key;
-    if (cut > 0 && yy - xx < cut) {
-        key = (u64)P.ns << P.sshift;                      // sentinel strip: sorts behind every active row
-    } else {
-        u32 up = (u32)((xx - yy) - P.ubase);
-        u32 vp = (u32)((xx + yy) - P.vbase);
-        u32 sv = vp / (u32)P.eps;
-        u32 vm = vp - sv * (u32)P.eps;
-        key = ((u64)sv << P.sshift) | ((u64)up << P.be) | (u64)vm;
+                                                   u64* __restrict__ keys, u32* __restrict__ rows_or_rank, int* __restrict__ cnt,
+                                                   int* __restrict__ cnt_tail) {
+    const int i0 = blockIdx.x * 1024 + threadIdx.x;       // four rows per thread, 256 apart: loads and atomics overlap
+    int xx[4], yy[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = i0 + 256 * k;
+        if (i < P.n) { xx[k] = __ldg(x + i); yy[k] = __ldg(y + i); }
     }
-    keys[i] = key;
-    rows[i] = (u32)i;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = i0 + 256 * k;
+        if (i >= P.n) continue;
+        u64 key;
+        u32 aux = (u32)i;
+        if (cut > 0 && yy[k] - xx[k] < cut) {
+            key = (u64)P.ns << P.sshift;                  // sentinel strip: sorts behind every active row
+            if (RANK) aux = (u32)atomicAdd(cnt_tail, 1);
+        } else {
+            u32 up = (u32)((xx[k] - yy[k]) - P.ubase);
+            u32 vp = (u32)((xx[k] + yy[k]) - P.vbase);
+            u32 sv = vp / (u32)P.eps;
+            u32 vm = vp - sv * (u32)P.eps;
+            key = ((u64)sv << P.sshift) | ((u64)up << P.be) | (u64)vm;
+            if (RANK) aux = (u32)atomicAdd(cnt + sv + 1, 1);
+        }
+        keys[i] = key;
+        rows_or_rank[i] = aux;
+    }
 }
 
-// sstart[k] = first sorted index whose strip >= k-1, k in [0, ns+2]
-__global__ void __launch_bounds__(256) strip_table_gap_kernel(const u64* __restrict__ keys, GridParams P, int* __restrict__ sstart) {
+// out[0] = sum over strips of (rows in the strip)^2 = the work of strip_rank_kernel; out[1] = longest strip (its critical path)
+__global__ void __launch_bounds__(256) strip_sumsq_kernel(const int* __restrict__ cnt, int m, unsigned long long* __restrict__ out) {
+    unsigned long long acc = 0, mx = 0;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < m; k += gridDim.x * blockDim.x) {
+        const unsigned long long c = (unsigned long long)cnt[k];
+        acc += c * c;
+        mx = max(mx, c);
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        acc += __shfl_down_sync(0xffffffffu, acc, d);
+        mx = max(mx, __shfl_down_sync(0xffffffffu, mx, d));
+    }
+    if ((threadIdx.x & 31) == 0 && acc) {
+        atomicAdd(out, acc);
+        atomicMax(out + 1, mx);
+    }
+}
+
+// Establishes the destination window of one scatter launch in L2 with full-sector stores, so the 12-byte stores of
+// the scatter merge into resident lines instead of each fetching its sector from DRAM first.
+__global__ void __launch_bounds__(256) strip_window_clear_kernel(const int* __restrict__ sstart, GridParams P, int s_lo, int s_hi,
+                                                                 u64* __restrict__ keys_out, u32* __restrict__ rows_out) {
+    const int a = s_lo >= P.ns ? P.n_act : __ldg(sstart + s_lo + 1);
+    const int b = s_hi > P.ns ? P.n : __ldg(sstart + s_hi + 1);
+    for (int j = a + blockIdx.x * blockDim.x + threadIdx.x; j < b; j += gridDim.x * blockDim.x) {
+        keys_out[j] = 0ull;
+        rows_out[j] = 0u;
+    }
+}
+
+// Row i goes to (start of its strip) + (its arrival rank): the strips are contiguous afterwards, in arrival order
+// inside.  A scatter over the whole destination would turn every 12-byte store into its own DRAM sector
+// read-modify-write (measured: 343 MB written for 120 MB of payload); so the destination is cut into nwin windows
+// of a few dozen MB that stay in L2 until their sectors are complete, one launch per window, and each launch
+// streams the keys past (evict-first loads) and stores only the rows of its window.
+__global__ void __launch_bounds__(256) strip_scatter_kernel(const u64* __restrict__ keys_in, const u32* __restrict__ rank,
+                                                            const int* __restrict__ sstart, GridParams P, int s_lo, int s_hi,
+                                                            u64* __restrict__ keys_out, u32* __restrict__ rows_out) {
+    const int i0 = blockIdx.x * 2048 + threadIdx.x;       // eight rows per thread, 256 apart
+    u64 key[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int i = i0 + 256 * k;
+        key[k] = i < P.n ? __ldcs(keys_in + i) : ~0ull;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int i = i0 + 256 * k;
+        const int s = (int)(key[k] >> P.sshift);
+        if (i >= P.n || s < s_lo || s >= s_hi) continue;
+        const int dest = (s >= P.ns ? P.n_act : __ldg(sstart + s + 1)) + (int)__ldcs(rank + i);
+        keys_out[dest] = key[k];
+        rows_out[dest] = (u32)i;
+    }
+}
+
+// Final position inside the strip = number of rows of the strip that sort before this one by (u', row) -- exactly the
+// order a stable radix sort of the (strip, u') bits over rows in row order produces.  A CTA owns 256 consecutive
+// positions; the strips they belong to are one contiguous range, staged in shared memory as (u', row); lanes of a
+// warp mostly share a strip, so the scan over the strip is a broadcast read.  A strip holds a few dozen rows at
+// ChIA-PET / HiChIP density (index_build checks the total work first); ranges that do not fit are scanned in
+// global memory.
+#define SR_CAP 3072
+#define SR_TILE 512
+__global__ void __launch_bounds__(256) strip_rank_kernel(const u64* __restrict__ keys_in, const u32* __restrict__ rows_in,
+                                                         const int* __restrict__ sstart, GridParams P, u64* __restrict__ keys_out,
+                                                         u32* __restrict__ rows_out) {
+    __shared__ u32 U[SR_CAP];
+    __shared__ u32 R[SR_CAP];
+    __shared__ int s_a0, s_b0;
+    const int p0 = blockIdx.x * SR_TILE;
+    if (p0 >= P.n_act) {                                   // rows behind n_act (cut filter) keep their place
+        for (int p = p0 + threadIdx.x; p < min(p0 + SR_TILE, P.n); p += 256) { keys_out[p] = keys_in[p]; rows_out[p] = rows_in[p]; }
+        return;
+    }
+    const int plast = min(p0 + SR_TILE, P.n_act) - 1;
+    if (threadIdx.x == 0) s_a0 = __ldg(sstart + (int)(keys_in[p0] >> P.sshift) + 1);
+    if (threadIdx.x == 32) s_b0 = __ldg(sstart + (int)(keys_in[plast] >> P.sshift) + 2);
+    __syncthreads();
+    const int a0 = s_a0, b0 = s_b0;
+    const bool staged = b0 - a0 <= SR_CAP;                 // CTA-uniform
+    if (staged) {
+        for (int j = a0 + threadIdx.x; j < b0; j += 256) {
+            U[j - a0] = (u32)(keys_in[j] >> P.be) & P.umask;
+            R[j - a0] = rows_in[j];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int h = 0; h < SR_TILE / 256; ++h) {
+        const int p = p0 + 256 * h + threadIdx.x;
+        if (p >= P.n) break;
+        const u64 key = keys_in[p];
+        const u32 row = rows_in[p];
+        int dest = p;
+        if (p < P.n_act) {
+            const int s = (int)(key >> P.sshift);
+            const int a = __ldg(sstart + s + 1), b = __ldg(sstart + s + 2);
+            const u32 my = (u32)(key >> P.be) & P.umask;
+            int c = 0;
+            if (staged) {
+#pragma unroll 4
+                for (int j = a - a0; j < b - a0; ++j) {
+                    const u32 uj = U[j];
+                    c += uj < my ? 1 : 0;
+                    if (uj == my) c += R[j] < row ? 1 : 0;
+                }
+            } else {
+                for (int j = a; j < b; ++j) {
+                    const u32 uj = (u32)(keys_in[j] >> P.be) & P.umask;
+                    if (uj < my) ++c;
+                    else if (uj == my && rows_in[j] < row) ++c;
+                }
+            }
+            dest = a + c;
+        }
+        keys_out[dest] = key;
+        rows_out[dest] = row;
+    }
+}
+
+__global__ void __launch_bounds__(256) iota_kernel(u32* __restrict__ rows, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i > P.n_act) return;
-    int cur = (i < P.n_act) ? (int)((keys[i] & KEY_MASK) >> P.sshift) : P.ns + 1;
-    int prev = (i > 0) ? (int)((keys[i - 1] & KEY_MASK) >> P.sshift) : -2;
-    for (int k = prev + 2; k <= cur + 1; ++k) sstart[k] = i;
+    if (i < n) rows[i] = (u32)i;
 }
 
+// sstart[k] = first sorted index whose strip >= k-1, k in [0, ns+2]  (sparse tables: one binary search per entry)
 __global__ void __launch_bounds__(256) strip_table_search_kernel(const u64* __restrict__ keys, GridParams P, int* __restrict__ sstart) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k > P.ns + 2) return;
@@ -524,20 +660,68 @@ int index_build(const int32_t* d_x, const int32_t* d_y, int64_t n, int32_t eps, 
     ix->rows = r1;
     RET_IF(tmp.alloc(&k0, n));
     RET_IF(tmp.alloc(&r0, n));
-    LAUNCH(pack_kernel, cdiv(n, 256), 256, 0, st, d_x, d_y, cut, P, k0, r0);
-    stage_mark("pack", st);
-    size_t sort_bytes = 0;
-    int begin_bit = P.be, end_bit = P.be + P.bu + P.bs;
-    CU_TRY(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, k0, k1, r0, r1, (int)n, begin_bit, end_bit, st));
-    void* d_sort;
-    RET_IF(tmp.alloc((char**)&d_sort, sort_bytes));
-    CU_TRY(cub::DeviceRadixSort::SortPairs(d_sort, sort_bytes, k0, k1, r0, r1, (int)n, begin_bit, end_bit, st));
-    stage_mark("sort", st);
     CU_TRY(cudaMallocAsync((void**)&ix->sstart, (size_t)(P.ns + 3) * sizeof(int), st));
-    if ((long long)P.ns > 4LL * P.n_act + 1024) {
+    const int begin_bit = P.be, end_bit = P.be + P.bu + P.bs;
+    // Order wanted: (strip, u'), ties in row order.  When the strip table is not much larger than the data, a counting
+    // sort by strip does it in three light passes: pack (+ one atomic per row: strip histogram and arrival rank), an
+    // exclusive scan of the histogram (= the strip table), a scatter next to the strip, and a rank inside the strip.
+    // The rank pass costs (rows per strip)^2, so its total work is checked first; long strips (Hi-C density) and
+    // sparse tables take the radix sort.
+    bool counted = false;
+    if ((long long)P.ns <= 4LL * P.n_act + 1024) {
+        u64* k2;
+        u32* r2;
+        unsigned long long* d_sumsq;
+        RET_IF(tmp.alloc(&k2, n));
+        RET_IF(tmp.alloc(&r2, n));
+        RET_IF(tmp.alloc(&d_sumsq, 3));
+        int* cnt = ix->sstart;                                   // scanned in place
+        CU_TRY(cudaMemsetAsync(cnt, 0, (size_t)(P.ns + 3) * sizeof(int), st));
+        CU_TRY(cudaMemsetAsync(d_sumsq, 0, 3 * sizeof(unsigned long long), st));
+        LAUNCH(pack_kernel<true>, cdiv(n, 1024), 256, 0, st, d_x, d_y, cut, P, k0, r0, cnt, reinterpret_cast<int*>(d_sumsq + 2));
+        stage_mark("pack", st);
+        LAUNCH(strip_sumsq_kernel, std::min(cdiv(P.ns + 3, 256), 148 * 8), 256, 0, st, cnt, P.ns + 3, d_sumsq);
+        size_t scan_bytes = 0;
+        CU_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, cnt, cnt, P.ns + 3, st));
+        void* d_scan;
+        RET_IF(tmp.alloc((char**)&d_scan, scan_bytes));
+        CU_TRY(cub::DeviceScan::ExclusiveSum(d_scan, scan_bytes, cnt, cnt, P.ns + 3, st));
+        unsigned long long sumsq[2] = {0, 0};
+        CU_TRY(cudaMemcpyAsync(sumsq, d_sumsq, sizeof(sumsq), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        stage_mark("strips", st);
+        if (sumsq[0] <= 192ull * (unsigned long long)P.n_act && sumsq[1] <= 4096ull) {   // break-even against the radix sort is near 250
+            // two 60 MB windows for 10 M rows measured best (24 MB: +0.07 ms of re-reads, one 120 MB window: +0.15 ms)
+            const long long win_bytes = 60LL << 20;
+            const int nwin = (int)std::min<long long>(8, std::max<long long>(1, (12LL * n + win_bytes - 1) / win_bytes));
+            for (int w = 0; w < nwin; ++w) {                     // strips are evenly filled: equal strip ranges ~ equal bytes
+                const int s_lo = (int)((long long)P.ns * w / nwin);
+                const int s_hi = w + 1 == nwin ? P.ns + 1 : (int)((long long)P.ns * (w + 1) / nwin);
+                LAUNCH(strip_window_clear_kernel, 148 * 4, 256, 0, st, ix->sstart, P, s_lo, s_hi, k2, r2);
+                LAUNCH(strip_scatter_kernel, cdiv(n, 2048), 256, 0, st, k0, r0, ix->sstart, P, s_lo, s_hi, k2, r2);
+            }
+            LAUNCH(strip_rank_kernel, cdiv(n, SR_TILE), 256, 0, st, k2, r2, ix->sstart, P, k1, r1);
+        } else {
+            LAUNCH(iota_kernel, cdiv(n, 256), 256, 0, st, r0, (int)n);
+            size_t sort_bytes = 0;
+            CU_TRY(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, k0, k1, r0, r1, (int)n, begin_bit, end_bit, st));
+            void* d_sort;
+            RET_IF(tmp.alloc((char**)&d_sort, sort_bytes));
+            CU_TRY(cub::DeviceRadixSort::SortPairs(d_sort, sort_bytes, k0, k1, r0, r1, (int)n, begin_bit, end_bit, st));
+        }
+        stage_mark("sort", st);
+        counted = true;
+    }
+    if (!counted) {
+        LAUNCH(pack_kernel<false>, cdiv(n, 1024), 256, 0, st, d_x, d_y, cut, P, k0, r0, (int*)nullptr, (int*)nullptr);
+        stage_mark("pack", st);
+        size_t sort_bytes = 0;
+        CU_TRY(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, k0, k1, r0, r1, (int)n, begin_bit, end_bit, st));
+        void* d_sort;
+        RET_IF(tmp.alloc((char**)&d_sort, sort_bytes));
+        CU_TRY(cub::DeviceRadixSort::SortPairs(d_sort, sort_bytes, k0, k1, r0, r1, (int)n, begin_bit, end_bit, st));
+        stage_mark("sort", st);
         LAUNCH(strip_table_search_kernel, cdiv(P.ns + 3, 256), 256, 0, st, ix->keys, P, ix->sstart);
-    } else {
-        LAUNCH(strip_table_gap_kernel, cdiv(P.n_act + 1, 256), 256, 0, st, ix->keys, P, ix->sstart);
     }
     {
         const int ntiles = cdiv(P.n_act, CT_TILE);

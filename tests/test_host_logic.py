@@ -236,3 +236,29 @@ def test_moment_combination_matches_numpy():
     mom = lambda v: (len(v), float(np.log2(v.astype(float)).mean()), float(((np.log2(v.astype(float)) - np.log2(v.astype(float)).mean()) ** 2).sum()))
     assert ests.cut_from_moments([mom(di[:1000]), mom(di[1000:])], [mom(dsv[:10]), mom(dsv[10:])], np.sort(dsv)) == ests.estIntSelCutFrag(di, dsv)
     assert ests.cut_from_moments([mom(di)], [mom(dsv[:5999])], np.sort(dsv[:5999])) == ests.estIntSelCutFrag(di, dsv[:5999])
+
+
+def test_scripts_common_windows_and_loop_parsing(gold_dir, tmp_path):
+    """scripts/_common: the batched window pairs equal getNearbyPairRegions pair by pair; preDs keeps the
+    significant loops of a .loop file in file order and finds iva/ivb by header."""
+    from cloops_b200.cModel import getNearbyPairRegions
+    from cloops_b200.scripts._common import loop_intervals, nearby_pairs, preDs
+    rng = np.random.default_rng(3)
+    a0 = rng.integers(0, 5000, 50)
+    b0 = a0 + rng.integers(100, 100000, 50)
+    iv = np.stack([a0, a0 + rng.integers(0, 3000, 50), b0, b0 + rng.integers(0, 3000, 50)], axis=1)
+    got = nearby_pairs(iv)
+    for m in range(len(iv)):
+        ivas, ivbs = getNearbyPairRegions([int(iv[m, 0]), int(iv[m, 1])], [int(iv[m, 2]), int(iv[m, 3])])
+        want = [[a[0], a[1], b[0], b[1]] for a in ivas for b in ivbs]
+        assert got[m].tolist() == want
+    (tmp_path / "chr21-chr21.jd").write_bytes(b"")
+    loop = os.path.join(gold_dir, "chr21_m1.loop")
+    rec = preDs(loop, str(tmp_path))
+    assert list(rec) == ["chr21"] and rec["chr21"]["f"].endswith("chr21-chr21.jd")
+    keys, chroms, ivs = loop_intervals(rec["chr21"]["rs"])
+    lines = [l.rstrip("\n").split("\t") for l in open(loop)][1:]
+    sig = [l for l in lines if float(l[-1]) >= 1]
+    assert keys == [l[0] for l in sig] and len(keys) == 202
+    assert ["%s:%d-%d" % (c, r[0], r[1]) for c, r in zip(chroms, ivs)] == [l[10] for l in sig]
+    assert preDs(loop, str(tmp_path / "missing")) == {}
