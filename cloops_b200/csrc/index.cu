@@ -668,7 +668,8 @@ int index_build(const int32_t* d_x, const int32_t* d_y, int64_t n, int32_t eps, 
     // The rank pass costs (rows per strip)^2, so its total work is checked first; long strips (Hi-C density) and
     // sparse tables take the radix sort.
     bool counted = false;
-    if ((long long)P.ns <= 4LL * P.n_act + 1024) {
+    const bool force_radix = getenv("CLOOPS_INDEX_SORT") != nullptr && strcmp(getenv("CLOOPS_INDEX_SORT"), "radix") == 0;   // test knob
+    if (!force_radix && (long long)P.ns <= 4LL * P.n_act + 1024) {
         u64* k2;
         u32* r2;
         unsigned long long* d_sumsq;

@@ -115,3 +115,37 @@ def test_refusals(dev):
         dev.dbscan_device(x, x.clone(), 100, 2, 7)               # unknown variant
     # the context stays healthy after refusals
     _check(dev, [1, 2, 3], [4, 5, 6], 10, 2)
+
+
+def test_index_order_counting_sort_equals_radix_sort(dev, monkeypatch):
+    """index_build has two ways to reach the (strip, u', row) order: the counting sort by strip (histogram + arrival
+    ranks, windowed scatter, in-strip rank) and the stable radix sort it falls back to for long strips.  Both must
+    produce the same index: coordinates in index order, neighbour counts and labels, with and without the cut
+    filter, on ties-heavy input too."""
+    from cloops_b200 import synth
+    rng = np.random.default_rng(5)
+    sets = []
+    X, Y = synth.chromosome(300_000, 8_000_000, seed=3, loop_frac=0.1, sigma=400.0)
+    sets.append((X, Y, 1000, 5, 0))
+    sets.append((X, Y, 1000, 5, 3000))
+    Xd = (rng.integers(0, 3000, 200_000) * 64).astype(np.int32)            # heavy duplicates / ties in (strip, u')
+    Yd = Xd + (rng.integers(0, 50, 200_000) * 64).astype(np.int32)
+    sets.append((Xd, Yd, 500, 4, 0))
+    for X, Y, eps, mp, cut in sets:
+        dx, dy = dev.to_device_i32(X), dev.to_device_i32(Y)
+        out = []
+        for mode in (None, "radix"):
+            if mode:
+                monkeypatch.setenv("CLOOPS_INDEX_SORT", mode)
+            else:
+                monkeypatch.delenv("CLOOPS_INDEX_SORT", raising=False)
+            ix = dev.Index(dx, dy, eps, cut)
+            xs, ys = ix.coords()
+            cnt = ix.count(mp)
+            lab, ls, info = ix.dbscan(mp, 2, want_sorted=True)
+            n = ix.n_active
+            out.append((xs[:n].cpu().numpy(), ys[:n].cpu().numpy(), cnt[:n].cpu().numpy(), lab.cpu().numpy(), ls.cpu().numpy()))
+            ix.close()
+        monkeypatch.delenv("CLOOPS_INDEX_SORT", raising=False)
+        for a, b in zip(*out):
+            assert np.array_equal(a, b)
