@@ -668,7 +668,9 @@ int index_build(const int32_t* d_x, const int32_t* d_y, int64_t n, int32_t eps, 
     // The rank pass costs (rows per strip)^2, so its total work is checked first; long strips (Hi-C density) and
     // sparse tables take the radix sort.
     bool counted = false;
-    const bool force_radix = getenv("CLOOPS_INDEX_SORT") != nullptr && strcmp(getenv("CLOOPS_INDEX_SORT"), "radix") == 0;   // test knob
+    const char* knob = getenv("CLOOPS_INDEX_SORT");                                       // test / measurement knob
+    const bool force_radix = knob != nullptr && strcmp(knob, "radix") == 0;
+    const bool force_count = knob != nullptr && strcmp(knob, "count") == 0;
     if (!force_radix && (long long)P.ns <= 4LL * P.n_act + 1024) {
         u64* k2;
         u32* r2;
@@ -691,7 +693,9 @@ int index_build(const int32_t* d_x, const int32_t* d_y, int64_t n, int32_t eps, 
         CU_TRY(cudaMemcpyAsync(sumsq, d_sumsq, sizeof(sumsq), cudaMemcpyDeviceToHost, st));
         CU_TRY(cudaStreamSynchronize(st));
         stage_mark("strips", st);
-        if (sumsq[0] <= 192ull * (unsigned long long)P.n_act && sumsq[1] <= 4096ull) {   // break-even against the radix sort is near 250
+        // measured on B200: the counting path wins up to ~80 rows per strip (10 M rows, 20 per strip: 0.56 vs 0.83 ms for the
+        // whole build; 41: 0.56 vs 0.70; 80: 1.17 vs 1.21; 160: 1.62 vs 1.21)
+        if ((force_count || sumsq[0] <= 64ull * (unsigned long long)P.n_act) && sumsq[1] <= 4096ull) {
             // two 60 MB windows for 10 M rows measured best (24 MB: +0.07 ms of re-reads, one 120 MB window: +0.15 ms)
             const long long win_bytes = 60LL << 20;
             const int nwin = (int)std::min<long long>(8, std::max<long long>(1, (12LL * n + win_bytes - 1) / win_bytes));
