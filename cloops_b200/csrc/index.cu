@@ -24,20 +24,35 @@ __global__ void extents_init_kernel(Extents* e) {
     e->umin = INT_MAX; e->umax = INT_MIN; e->vmin = INT_MAX; e->vmax = INT_MIN; e->n_act = 0; e->overflow = 0;
 }
 
-__global__ void __launch_bounds__(256) extents_kernel(const int* __restrict__ x, const int* __restrict__ y, int n, int cut,
+__device__ __forceinline__ void extents_point(int xx, int yy, int cut, int& umin, int& umax, int& vmin, int& vmax, int& cnt, int& bad) {
+    if (xx < -(1 << 30) || xx >= (1 << 30) || yy < -(1 << 30) || yy >= (1 << 30)) { bad = 1; return; }   // u, v would leave int32
+    if (cut > 0 && yy - xx < cut) return;
+    const int u = xx - yy, v = xx + yy;
+    umin = min(umin, u); umax = max(umax, u); vmin = min(vmin, v); vmax = max(vmax, v);
+    ++cnt;
+}
+
+// vec: x and y are 16-byte aligned -> four rows per 128-bit load
+__global__ void __launch_bounds__(256) extents_kernel(const int* __restrict__ x, const int* __restrict__ y, int n, int cut, int vec,
                                                       Extents* out) {
-    int umin = INT_MAX, umax = INT_MIN, vmin = INT_MAX, vmax = INT_MIN, cnt = 0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        int xx = __ldg(x + i), yy = __ldg(y + i);
-        if (xx < -(1 << 30) || xx >= (1 << 30) || yy < -(1 << 30) || yy >= (1 << 30)) {
-            out->overflow = 1;                            // rotated coordinates would leave int32
-            continue;
+    int umin = INT_MAX, umax = INT_MIN, vmin = INT_MAX, vmax = INT_MIN, cnt = 0, bad = 0;
+    const int stride = gridDim.x * blockDim.x, t = blockIdx.x * blockDim.x + threadIdx.x;
+    int done = 0;
+    if (vec) {
+        const int n4 = n >> 2;
+        const int4* __restrict__ x4 = reinterpret_cast<const int4*>(x);
+        const int4* __restrict__ y4 = reinterpret_cast<const int4*>(y);
+        for (int i = t; i < n4; i += stride) {
+            const int4 a = __ldg(x4 + i), b = __ldg(y4 + i);
+            extents_point(a.x, b.x, cut, umin, umax, vmin, vmax, cnt, bad);
+            extents_point(a.y, b.y, cut, umin, umax, vmin, vmax, cnt, bad);
+            extents_point(a.z, b.z, cut, umin, umax, vmin, vmax, cnt, bad);
+            extents_point(a.w, b.w, cut, umin, umax, vmin, vmax, cnt, bad);
         }
-        if (cut > 0 && yy - xx < cut) continue;
-        int u = xx - yy, v = xx + yy;
-        umin = min(umin, u); umax = max(umax, u); vmin = min(vmin, v); vmax = max(vmax, v);
-        ++cnt;
+        done = n4 << 2;
     }
+    for (int i = done + t; i < n; i += stride) extents_point(__ldg(x + i), __ldg(y + i), cut, umin, umax, vmin, vmax, cnt, bad);
+    if (bad) out->overflow = 1;
     umin = __reduce_min_sync(0xffffffffu, umin);
     umax = __reduce_max_sync(0xffffffffu, umax);
     vmin = __reduce_min_sync(0xffffffffu, vmin);
@@ -617,7 +632,8 @@ int index_build(const int32_t* d_x, const int32_t* d_y, int64_t n, int32_t eps, 
     RET_IF(tmp.alloc(&d_ext, 1));
     LAUNCH(extents_init_kernel, 1, 1, 0, st, d_ext);
     int grid = std::min(cdiv(n, 256), 148 * 8);
-    LAUNCH(extents_kernel, grid, 256, 0, st, d_x, d_y, (int)n, cut, d_ext);
+    const int vec = ((((uintptr_t)d_x) | ((uintptr_t)d_y)) & 15) == 0 ? 1 : 0;
+    LAUNCH(extents_kernel, grid, 256, 0, st, d_x, d_y, (int)n, cut, vec, d_ext);
     Extents ext;
     CU_TRY(cudaMemcpyAsync(&ext, d_ext, sizeof(ext), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
