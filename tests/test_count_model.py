@@ -1,4 +1,4 @@
-"""CPU model of the region-query kernel (cloops_b200/csrc/index.cu:count_kernel_tiled), checked against
+"""CPU model of the region-query kernel (cloops_b200/csrc/region_query.cu:count_kernel_tiled), checked against
 the oracle's neighbour counts.  It restates, tile by tile, exactly the integer algebra the kernel relies
 on -- padded u', W = (relative strip << bu) | u' with one-compare window tests, guard words instead of
 bounds tests, slots that keep the global index modulo 4, the per-tile header, the uniform (fixed trip
