@@ -481,6 +481,7 @@ int index_dbscan(cloops_index* ix, int minPts, int variant, int* d_labels, int* 
     W.slots_lab = W.counters + 8 + CTR_SLOTS * CTR_STRIDE;
     CU_TRY(cudaMemsetAsync(W.flags, 0, ((size_t)P.n + 1) * sizeof(int), st));
 
+    stage_mark("workspace", st);                 // allocations + the two memsets above, so that "region_query" times the kernel alone
     RET_IF(index_count(ix, minPts, W.cnt, st));
     stage_mark("region_query", st);
     LAUNCH(flag_kernel, g, 256, 0, st, ix->keys, P, minPts, W, v2 ? 1 : 0);
