@@ -203,11 +203,16 @@ __global__ void __launch_bounds__(256) strip_rank_kernel(const u64* __restrict__
             const u32 my = (u32)(key >> P.be) & P.umask;
             int c = 0;
             if (staged) {
+                int eq = 0;                                       // rows of the strip with the same u' (this one included)
 #pragma unroll 4
                 for (int j = a - a0; j < b - a0; ++j) {
                     const u32 uj = U[j];
-                    c += uj < my ? 1 : 0;
-                    if (uj == my) c += R[j] < row ? 1 : 0;
+                    asm("{\n\t.reg .pred p, q;\n\tsetp.lt.u32 p, %2, %3;\n\tsetp.eq.u32 q, %2, %3;\n\t@p add.s32 %0, %0, 1;\n\t@q add.s32 %1, %1, 1;\n\t}"
+                        : "+r"(c), "+r"(eq) : "r"(uj), "r"(my));
+                }
+                if (eq > 1) {                                     // ties are rare: a second pass orders them by row
+                    for (int j = a - a0; j < b - a0; ++j)
+                        if (U[j] == my && R[j] < row) ++c;
                 }
             } else {
                 for (int j = a; j < b; ++j) {
