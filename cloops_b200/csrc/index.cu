@@ -324,8 +324,8 @@ int index_build(const int32_t* d_x, const int32_t* d_y, int64_t n, int32_t eps, 
     CU_TRY(cudaMallocAsync((void**)&ix->sstart, (size_t)(P.ns + 3) * sizeof(int), st));
     const int begin_bit = P.be, end_bit = P.be + P.bu + P.bs;
     // Order wanted: (strip, u'), ties in row order.  When the strip table is not much larger than the data, a counting
-    // sort by strip does it in three light passes: pack (+ one atomic per row: strip histogram and arrival rank), an
-    // exclusive scan of the histogram (= the strip table), a scatter next to the strip, and a rank inside the strip.
+    // sort by strip does it in light passes: pack (+ one fire-and-forget atomic per row: the strip histogram), an exclusive
+    // scan of the histogram (= the strip table), a scatter into the strip (one cursor atomic per row), a rank inside the strip.
     // The rank pass costs (rows per strip)^2, so its total work is checked first; long strips (Hi-C density) and
     // sparse tables take the radix sort.
     bool counted = false;
