@@ -149,3 +149,33 @@ def test_index_order_counting_sort_equals_radix_sort(dev, monkeypatch):
         monkeypatch.delenv("CLOOPS_INDEX_SORT", raising=False)
         for a, b in zip(*out):
             assert np.array_equal(a, b)
+
+
+def test_region_query_tile_boundaries_and_unaligned_output(dev):
+    """The tiled region query owns 1024 sorted points per CTA (4 per thread, 128-bit stores): sizes around the tile and
+    vector boundaries, every templated cap, and an output pointer that is not 16-byte aligned."""
+    rng = np.random.default_rng(9)
+    for n in (1, 3, 4, 5, 1023, 1024, 1025, 2047, 2048, 2049, 4100):
+        X = rng.integers(0, 40 * max(n, 8), n)
+        Y = X + rng.integers(0, 3000, n)
+        eps = 700
+        want = spec.neighbour_counts(X.astype(np.int64), Y.astype(np.int64), eps)
+        dx, dy = dev.to_device_i32(X), dev.to_device_i32(Y)
+        ix = dev.Index(dx, dy, eps)
+        row_of = None
+        for cap in (0, 1, 2, 3, 5, 6, 9, 10, 17):
+            out = ix.count(cap)[:ix.n_active].cpu().numpy()
+            buf = torch.full((ix.n_active + 5,), -3, dtype=torch.int32, device=dx.device)
+            ix.count(cap, buf[1:])                                   # 4-byte aligned only
+            assert np.array_equal(buf[1:1 + ix.n_active].cpu().numpy(), out)
+            assert int(buf[0]) == -3 and int(buf[1 + ix.n_active]) == -3
+            # index order -> row order through the coordinates (duplicates share their count, so any matching row will do)
+            if row_of is None:
+                xs, ys = ix.coords()
+                key = {}
+                for r, (a, b) in enumerate(zip(X.tolist(), Y.tolist())):
+                    key.setdefault((a, b), r)
+                row_of = np.array([key[(a, b)] for a, b in zip(xs.cpu().numpy().tolist(), ys.cpu().numpy().tolist())])
+            exp = want[row_of] if cap == 0 else np.minimum(want[row_of], cap)
+            assert np.array_equal(out, exp), (n, cap)
+        ix.close()
