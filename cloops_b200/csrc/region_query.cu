@@ -78,7 +78,10 @@ __device__ __forceinline__ int count_point_global(const u64* __restrict__ keys, 
 //    strip), no per-lane bounds -- running past the strip's end is harmless because W keeps ascending --
 //    so one step is load / compare / predicated add, without divergence.  Then 4 predicated probes and
 //    a tail loop for the rare longer windows.
-//  * Counts leave the CTA as coalesced 128-bit stores.
+//  * The counts phase 1 settles (own strip saturates, or cap reached) leave the CTA as coalesced 128-bit stores straight
+//    from registers; phase 2 overwrites its points' counts afterwards (same CTA, ordered by the barrier in between).
+//  * One 16-byte header per tile (TileInfo, written once per index) replaces the dependent prologue key -> strip ->
+//    strip table: the kernel starts with one broadcast load and has three barriers in all.
 // Tiles whose staged range does not fit (very long strips: dense Hi-C diagonals, where the own strip
 // saturates at once) fall back to count_point_global.
 #define CT_THREADS 256
