@@ -81,7 +81,7 @@ __device__ __forceinline__ int count_point_global(const u64* __restrict__ keys, 
 //  * The counts phase 1 settles (own strip saturates, or cap reached) leave the CTA as coalesced 128-bit stores straight
 //    from registers; phase 2 overwrites its points' counts afterwards (same CTA, ordered by the barrier in between).
 //  * One 16-byte header per tile (TileInfo, written once per index) replaces the dependent prologue key -> strip ->
-//    strip table: the kernel starts with one broadcast load and has three barriers in all.
+//    strip table: the kernel starts with one broadcast load and has two barriers in all.
 // Tiles whose staged range does not fit (very long strips: dense Hi-C diagonals, where the own strip
 // saturates at once) fall back to count_point_global.
 #define CT_THREADS 256
