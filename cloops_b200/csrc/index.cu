@@ -66,11 +66,13 @@ __global__ void __launch_bounds__(256) extents_kernel(const int* __restrict__ x,
 }
 
 // Packs the key of every row.  RANK: also counts the rows of each strip (cnt[strip + 1], the layout of the strip
-// table; fire-and-forget atomics), so that one exclusive scan of cnt IS the strip table and the rows can be placed next
-// to their strip without a radix sort (index_build).
+// table) and remembers each row's arrival rank inside its strip, so that one exclusive scan of cnt IS the strip
+// table and the rows can be placed next to their strip without a radix sort (index_build).  Rows removed by the
+// cut filter are ranked behind the active ones through cnt_tail.
 template <bool RANK>
 __global__ void __launch_bounds__(256) pack_kernel(const int* __restrict__ x, const int* __restrict__ y, int cut, GridParams P,
-                                                   u64* __restrict__ keys, u32* __restrict__ rows, int* __restrict__ cnt) {
+                                                   u64* __restrict__ keys, u32* __restrict__ rows_or_rank, int* __restrict__ cnt,
+                                                   int* __restrict__ cnt_tail) {
     const int i0 = blockIdx.x * 1024 + threadIdx.x;       // four rows per thread, 256 apart: loads and atomics overlap
     int xx[4], yy[4];
 #pragma unroll
@@ -86,16 +88,17 @@ __global__ void __launch_bounds__(256) pack_kernel(const int* __restrict__ x, co
         u32 aux = (u32)i;
         if (cut > 0 && yy[k] - xx[k] < cut) {
             key = (u64)P.ns << P.sshift;                  // sentinel strip: sorts behind every active row
+            if (RANK) aux = (u32)atomicAdd(cnt_tail, 1);
         } else {
             u32 up = (u32)((xx[k] - yy[k]) - P.ubase);
             u32 vp = (u32)((xx[k] + yy[k]) - P.vbase);
             u32 sv = vp / (u32)P.eps;
             u32 vm = vp - sv * (u32)P.eps;
             key = ((u64)sv << P.sshift) | ((u64)up << P.be) | (u64)vm;
-            if (RANK) atomicAdd(cnt + sv + 1, 1);
+            if (RANK) aux = (u32)atomicAdd(cnt + sv + 1, 1);
         }
         keys[i] = key;
-        if (!RANK) rows[i] = aux;
+        rows_or_rank[i] = aux;
     }
 }
 
@@ -117,13 +120,27 @@ __global__ void __launch_bounds__(256) strip_sumsq_kernel(const int* __restrict_
     }
 }
 
-// Row i goes to the next free place of its strip (a cursor per strip): the strips are contiguous afterwards, in arrival order
+// Establishes the destination window of one scatter launch in L2 with full-sector stores, so the 12-byte stores of
+// the scatter merge into resident lines instead of each fetching its sector from DRAM first (measured: the sort stage
+// of config 2 takes 0.32 ms with it and 0.39 ms without).
+__global__ void __launch_bounds__(256) strip_window_clear_kernel(const int* __restrict__ sstart, GridParams P, int s_lo, int s_hi,
+                                                                 u64* __restrict__ keys_out, u32* __restrict__ rows_out) {
+    const int a = s_lo >= P.ns ? P.n_act : __ldg(sstart + s_lo + 1);
+    const int b = s_hi > P.ns ? P.n : __ldg(sstart + s_hi + 1);
+    for (int j = a + blockIdx.x * blockDim.x + threadIdx.x; j < b; j += gridDim.x * blockDim.x) {
+        keys_out[j] = 0ull;
+        rows_out[j] = 0u;
+    }
+}
+
+// Row i goes to (start of its strip) + (its arrival rank): the strips are contiguous afterwards, in arrival order
 // inside.  A scatter over the whole destination would turn every 12-byte store into its own DRAM sector
 // read-modify-write (measured: 343 MB written for 120 MB of payload); so the destination is cut into nwin windows
 // of a few dozen MB that stay in L2 until their sectors are complete, one launch per window, and each launch
 // streams the keys past (evict-first loads) and stores only the rows of its window.
-__global__ void __launch_bounds__(256) strip_scatter_kernel(const u64* __restrict__ keys_in, int* __restrict__ cursor, GridParams P,
-                                                            int s_lo, int s_hi, u64* __restrict__ keys_out, u32* __restrict__ rows_out) {
+__global__ void __launch_bounds__(256) strip_scatter_kernel(const u64* __restrict__ keys_in, const u32* __restrict__ rank,
+                                                            const int* __restrict__ sstart, GridParams P, int s_lo, int s_hi,
+                                                            u64* __restrict__ keys_out, u32* __restrict__ rows_out) {
     const int i0 = blockIdx.x * 2048 + threadIdx.x;       // eight rows per thread, 256 apart
     u64 key[8];
 #pragma unroll
@@ -136,9 +153,7 @@ __global__ void __launch_bounds__(256) strip_scatter_kernel(const u64* __restric
         const int i = i0 + 256 * k;
         const int s = (int)(key[k] >> P.sshift);
         if (i >= P.n || s < s_lo || s >= s_hi) continue;
-        // cursor[] starts as a copy of the strip table (entry ns + 1 = n_act: the rows removed by the cut filter follow
-        // the active ones); the value returned is the row's place, in arrival order inside its strip
-        const int dest = atomicAdd(cursor + min(s, P.ns) + 1, 1);
+        const int dest = (s >= P.ns ? P.n_act : __ldg(sstart + s + 1)) + (int)__ldcs(rank + i);
         keys_out[dest] = key[k];
         rows_out[dest] = (u32)i;
     }
@@ -324,8 +339,8 @@ int index_build(const int32_t* d_x, const int32_t* d_y, int64_t n, int32_t eps, 
     CU_TRY(cudaMallocAsync((void**)&ix->sstart, (size_t)(P.ns + 3) * sizeof(int), st));
     const int begin_bit = P.be, end_bit = P.be + P.bu + P.bs;
     // Order wanted: (strip, u'), ties in row order.  When the strip table is not much larger than the data, a counting
-    // sort by strip does it in light passes: pack (+ one fire-and-forget atomic per row: the strip histogram), an exclusive
-    // scan of the histogram (= the strip table), a scatter into the strip (one cursor atomic per row), a rank inside the strip.
+    // sort by strip does it in light passes: pack (+ one atomic per row: strip histogram and arrival rank), an exclusive scan
+    // of the histogram (= the strip table), a scatter next to the strip, and a rank inside the strip.
     // The rank pass costs (rows per strip)^2, so its total work is checked first; long strips (Hi-C density) and
     // sparse tables take the radix sort.
     bool counted = false;
@@ -338,11 +353,11 @@ int index_build(const int32_t* d_x, const int32_t* d_y, int64_t n, int32_t eps, 
         unsigned long long* d_sumsq;
         RET_IF(tmp.alloc(&k2, n));
         RET_IF(tmp.alloc(&r2, n));
-        RET_IF(tmp.alloc(&d_sumsq, 2));
+        RET_IF(tmp.alloc(&d_sumsq, 3));
         int* cnt = ix->sstart;                                   // scanned in place
         CU_TRY(cudaMemsetAsync(cnt, 0, (size_t)(P.ns + 3) * sizeof(int), st));
-        CU_TRY(cudaMemsetAsync(d_sumsq, 0, 2 * sizeof(unsigned long long), st));
-        LAUNCH(pack_kernel<true>, cdiv(n, 1024), 256, 0, st, d_x, d_y, cut, P, k0, r0, cnt);
+        CU_TRY(cudaMemsetAsync(d_sumsq, 0, 3 * sizeof(unsigned long long), st));
+        LAUNCH(pack_kernel<true>, cdiv(n, 1024), 256, 0, st, d_x, d_y, cut, P, k0, r0, cnt, reinterpret_cast<int*>(d_sumsq + 2));
         stage_mark("pack", st);
         LAUNCH(strip_sumsq_kernel, std::min(cdiv(P.ns + 3, 256), 148 * 8), 256, 0, st, cnt, P.ns + 3, d_sumsq);
         size_t scan_bytes = 0;
@@ -357,16 +372,14 @@ int index_build(const int32_t* d_x, const int32_t* d_y, int64_t n, int32_t eps, 
         // measured on B200: the counting path wins up to ~80 rows per strip (10 M rows, 20 per strip: 0.56 vs 0.83 ms for the
         // whole build; 41: 0.56 vs 0.70; 80: 1.17 vs 1.21; 160: 1.62 vs 1.21)
         if ((force_count || sumsq[0] <= 64ull * (unsigned long long)P.n_act) && sumsq[1] <= 4096ull) {
-            int* cursor;
-            RET_IF(tmp.alloc(&cursor, (size_t)P.ns + 3));
-            CU_TRY(cudaMemcpyAsync(cursor, ix->sstart, (size_t)(P.ns + 3) * sizeof(int), cudaMemcpyDeviceToDevice, st));
             // two 60 MB windows for 10 M rows measured best (24 MB: +0.07 ms of re-reads, one 120 MB window: +0.15 ms)
             const long long win_bytes = 60LL << 20;
             const int nwin = (int)std::min<long long>(8, std::max<long long>(1, (12LL * n + win_bytes - 1) / win_bytes));
             for (int w = 0; w < nwin; ++w) {                     // strips are evenly filled: equal strip ranges ~ equal bytes
                 const int s_lo = (int)((long long)P.ns * w / nwin);
                 const int s_hi = w + 1 == nwin ? P.ns + 1 : (int)((long long)P.ns * (w + 1) / nwin);
-                LAUNCH(strip_scatter_kernel, cdiv(n, 2048), 256, 0, st, k0, cursor, P, s_lo, s_hi, k2, r2);
+                LAUNCH(strip_window_clear_kernel, 148 * 4, 256, 0, st, ix->sstart, P, s_lo, s_hi, k2, r2);
+                LAUNCH(strip_scatter_kernel, cdiv(n, 2048), 256, 0, st, k0, r0, ix->sstart, P, s_lo, s_hi, k2, r2);
             }
             LAUNCH(strip_rank_kernel, cdiv(n, SR_TILE), 256, 0, st, k2, r2, ix->sstart, P, k1, r1);
         } else {
@@ -381,7 +394,7 @@ int index_build(const int32_t* d_x, const int32_t* d_y, int64_t n, int32_t eps, 
         counted = true;
     }
     if (!counted) {
-        LAUNCH(pack_kernel<false>, cdiv(n, 1024), 256, 0, st, d_x, d_y, cut, P, k0, r0, (int*)nullptr);
+        LAUNCH(pack_kernel<false>, cdiv(n, 1024), 256, 0, st, d_x, d_y, cut, P, k0, r0, (int*)nullptr, (int*)nullptr);
         stage_mark("pack", st);
         size_t sort_bytes = 0;
         CU_TRY(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, k0, k1, r0, r1, (int)n, begin_bit, end_bit, st));
