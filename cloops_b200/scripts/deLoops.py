@@ -26,21 +26,17 @@ logger = None
 
 
 def deloopHelp(argv=None):
-    parser = argparse.ArgumentParser(description="Differentially enriched loops calling based on loops called by cLoops. "
-                                                 "For example: deLoops -fa a.loop -fb b.loop -da A -db B -p 10")
-    parser.add_argument("-fa", dest="fa", required=True, type=str,
-                        help="Loops file called by cLoops. Only using significant loops as mark 1, you can change this in the .loop file.")
-    parser.add_argument("-fb", dest="fb", required=True, type=str, help="Loops file called by cLoops.")
-    parser.add_argument("-da", dest="da", required=True, type=str,
-                        help="Directory for .jd files of loop file a, generated by cLoops with option -s 1.")
-    parser.add_argument("-db", dest="db", required=True, type=str,
-                        help="Directory for .jd files of loop file b, generated by cLoops with option -s 1.")
-    parser.add_argument("-p", dest="cpu", required=False, default=1, type=int,
-                        help="Kept for command-line compatibility; chromosomes run on the GPU one after the other.")
-    parser.add_argument("-c", dest="chroms", required=False, default="", type=str,
-                        help="Whether to process limited chroms, specify it as chr1,chr2,chr3, default is not.")
-    parser.add_argument("-dis", dest="dis", required=False, default=0, type=int,
-                        help="Set a distance cutoff to filter PETs, default is 0.")
+    """Same flags as cLoops/utils.py:207-262 (deloopHelp)."""
+    parser = argparse.ArgumentParser(description="Differentially enriched loops between two cLoops runs: "
+                                                 "deLoops -fa a.loop -fb b.loop -da A -db B")
+    jd = "directory with the %s sample's .jd files (written by cLoops -s 1)"
+    parser.add_argument("-fa", dest="fa", required=True, type=str, help=".loop file of sample a; loops marked significant (last column 1) are used")
+    parser.add_argument("-fb", dest="fb", required=True, type=str, help=".loop file of sample b")
+    parser.add_argument("-da", dest="da", required=True, type=str, help=jd % "a")
+    parser.add_argument("-db", dest="db", required=True, type=str, help=jd % "b")
+    parser.add_argument("-p", dest="cpu", default=1, type=int, help="accepted for compatibility; chromosomes run on the GPU in turn")
+    parser.add_argument("-c", dest="chroms", default="", type=str, help="restrict to these chromosomes, e.g. chr1,chr2")
+    parser.add_argument("-dis", dest="dis", default=0, type=int, help="drop PETs closer than this distance before counting (default 0)")
     return parser.parse_args(argv)
 
 
@@ -96,20 +92,15 @@ def main(argv=None):
     global logger
     logger = getLogger(os.path.join(os.getcwd(), "deLoops.log"))
     op = deloopHelp(argv)
-    chroms = [] if op.chroms == "" else set(op.chroms.split(","))
+    chroms = set(op.chroms.split(",")) if op.chroms else []
     ra = preDs(op.fa, op.da, chroms, logger=logger)
     rb = preDs(op.fb, op.db, chroms, logger=logger)
-    prea, preb = os.path.split(op.da)[1], os.path.split(op.db)[1]
-    keys = set(ra.keys()).intersection(set(rb.keys()))
-    for key in list(ra.keys()):
-        if key not in keys:
-            del ra[key]
-            logger.info("No match of %s in %s or %s" % (key, op.fa, op.da))
-    for key in list(rb.keys()):
-        if key not in keys:
-            del rb[key]
-            logger.info("No match of %s in %s or %s" % (key, op.fb, op.db))
-    callDeLoops(ra, rb, prea, preb, op.dis, op.cpu)
+    both = set(ra) & set(rb)                              # scripts/deLoops:196-205: chromosomes present in both samples
+    for recs, loops, jds in ((ra, op.fa, op.da), (rb, op.fa, op.da)):
+        for key in [k for k in recs if k not in both]:
+            del recs[key]
+            logger.info("No match of %s in %s or %s" % (key, loops, jds))
+    callDeLoops(ra, rb, os.path.split(op.da)[1], os.path.split(op.db)[1], op.dis, op.cpu)
 
 
 if __name__ == "__main__":

@@ -25,18 +25,15 @@ logger = None
 
 
 def help(argv=None):
-    parser = argparse.ArgumentParser(description="Quantify loops from cLoops called. For example: quantifyLoops.py -f a.loop -d A -o fout -p 10")
-    parser.add_argument("-f", dest="f", required=True, type=str,
-                        help="Loops file called by cLoops. Only using significant loops as mark 1, you can change this in the .loop file.")
-    parser.add_argument("-d", dest="d", required=True, type=str,
-                        help="Directory for .jd files of loop file a, generated by cLoops with option -s 1.")
-    parser.add_argument("-o", dest="output", required=True, type=str, help="Output file name prefix.")
-    parser.add_argument("-p", dest="cpu", required=False, default=1, type=int,
-                        help="Kept for command-line compatibility; chromosomes run on the GPU one after the other.")
-    parser.add_argument("-c", dest="chroms", required=False, default="", type=str,
-                        help="Whether to process limited chroms, specify it as chr1,chr2,chr3, default is not.")
-    parser.add_argument("-dis", dest="dis", required=False, default=0, type=int,
-                        help="Set a distance cutoff to filter PETs, default is 0.")
+    """Same flags as scripts/quantifyLoops.py:29-89."""
+    parser = argparse.ArgumentParser(description="Quantify the significant loops of a cLoops run against a set of PETs: "
+                                                 "quantifyLoops -f a.loop -d A -o fout")
+    parser.add_argument("-f", dest="f", required=True, type=str, help=".loop file; loops marked significant (last column 1) are used")
+    parser.add_argument("-d", dest="d", required=True, type=str, help="directory with the sample's .jd files (written by cLoops -s 1)")
+    parser.add_argument("-o", dest="output", required=True, type=str, help="prefix of the output table")
+    parser.add_argument("-p", dest="cpu", default=1, type=int, help="accepted for compatibility; chromosomes run on the GPU in turn")
+    parser.add_argument("-c", dest="chroms", default="", type=str, help="restrict to these chromosomes, e.g. chr1,chr2")
+    parser.add_argument("-dis", dest="dis", default=0, type=int, help="drop PETs closer than this distance before counting (default 0)")
     return parser.parse_args(argv)
 
 
