@@ -262,3 +262,26 @@ def test_scripts_common_windows_and_loop_parsing(gold_dir, tmp_path):
     assert keys == [l[0] for l in sig] and len(keys) == 202
     assert ["%s:%d-%d" % (c, r[0], r[1]) for c, r in zip(chroms, ivs)] == [l[10] for l in sig]
     assert preDs(loop, str(tmp_path / "missing")) == {}
+
+
+def test_deloops_main_keeps_chromosomes_present_in_both_samples(gold_dir, tmp_path, monkeypatch):
+    """scripts/deLoops:187-207: only chromosomes with loops AND a .jd file in both samples reach callDeLoops."""
+    from cloops_b200.scripts import deLoops
+    loop = os.path.join(gold_dir, "chr21_m1.loop")
+    lines = open(loop).read().split("\n")
+    extra = lines[1].replace("chr21", "chr22")                       # one significant loop on a chromosome only sample a has
+    fa = tmp_path / "a.loop"
+    fa.write_text("\n".join([lines[0], extra] + lines[1:]))
+    da, db = tmp_path / "A", tmp_path / "B"
+    da.mkdir()
+    db.mkdir()
+    for d, chroms in ((da, ("chr21", "chr22")), (db, ("chr21",))):
+        for c in chroms:
+            (d / ("%s-%s.jd" % (c, c))).write_bytes(b"")
+    seen = {}
+    monkeypatch.setattr(deLoops, "callDeLoops", lambda ra, rb, prea, preb, dis, cpu: seen.update(ra=ra, rb=rb, pre=(prea, preb), dis=dis))
+    monkeypatch.chdir(tmp_path)
+    deLoops.main(["-fa", str(fa), "-fb", loop, "-da", str(da), "-db", str(db), "-dis", "7"])
+    assert list(seen["ra"]) == ["chr21"] and list(seen["rb"]) == ["chr21"]
+    assert seen["pre"] == ("A", "B") and seen["dis"] == 7
+    assert len(seen["ra"]["chr21"]["rs"]) == 202
