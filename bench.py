@@ -86,7 +86,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(0.004)
 
     def stop(self):
         self._halt.set()
