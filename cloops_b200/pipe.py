@@ -274,11 +274,18 @@ def pipe(fs, fout, eps, minPts, chroms="", cpu=1, tmp=0, hic=0, washU=0, juice=0
     """cLoops/pipe.py:206-295."""
     log = _log()
     chroms = [] if chroms == "" else set(chroms.split(","))
-    if os.path.isdir(fout):
-        log.error("working directory %s exists, return." % fout)
+    # rank 0 alone looks at / creates the output directory and every rank follows its decision: a rank that
+    # checked isdir after rank 0's mkdir would otherwise leave while the others wait in a collective
+    ok = True
+    if dist.rank() == 0:
+        if os.path.isdir(fout):
+            log.error("working directory %s exists, return." % fout)
+            ok = False
+        else:
+            os.mkdir(fout)
+    if not dist.broadcast_object(ok):
         return
     if dist.rank() == 0:
-        os.mkdir(fout)
         if eps == 0:
             cfs, ds = parseRawBedpe(fs, fout, chroms, cut, log)
         else:

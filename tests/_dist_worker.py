@@ -81,3 +81,23 @@ assert cut == want, (cut, want)
 assert n_dis == sum(len(dist_i[f]) for f in used) and n_dss == sum(len(dist_s[f]) for f in used)
 got = dist.all_gather_concat(torch.arange(3 + dist.rank(), dtype=torch.int32))
 assert got.tolist() == [0, 1, 2, 0, 1, 2, 3]
+
+# pipe() itself under two ranks: rank 0 alone decides about the output directory and every rank follows.
+# (1) existing directory -> every rank returns, no collective is left hanging; (2) fresh directory -> the run completes.
+pipe.parseRawBedpe2 = lambda fs, fout, chroms, cut, log: list(files)
+calls = []
+orig_round = pipe._round
+pipe._round = lambda fs, ep, m, cut: (calls.append((ep, m, cut)), orig_round(fs, ep, m, cut))[1]
+exists = os.path.join(out, "exists")
+if dist.rank() == 0:
+    os.mkdir(exists)
+dist.barrier()
+assert pipe.pipe(["x.bedpe"], exists, [1000], [5]) is None and calls == []
+dist.barrier()
+fresh = os.path.join(out, "fresh")
+pipe.pipe(["x.bedpe"], fresh, [1000, 2000], [5], tmp=1)
+assert [c[:2] for c in calls] == [(1000, 5), (2000, 5)] and calls[1][2] == want, calls
+dist.barrier()
+if dist.rank() == 0:
+    assert os.path.isdir(fresh) and os.path.isfile(fresh + ".loop")
+    open(os.path.join(out, "ok_pipe"), "w").write("ok")

@@ -167,7 +167,7 @@ def test_two_rank_gloo(tmp_path):
            "--master-port", "29631", os.path.join(ROOT, "tests", "_dist_worker.py"), str(tmp_path)]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert (tmp_path / "ok").exists()
+    assert (tmp_path / "ok").exists() and (tmp_path / "ok_pipe").exists()
 
 
 def test_columnar_ingest_equals_line_parser(tmp_path):
