@@ -10,6 +10,7 @@ LIB_PATH = os.path.join(HERE, "libcloops_b200.so")
 
 V1, V2, BLOCK = 1, 2, 3
 VARIANTS = {"v1": V1, "v2": V2, "block": BLOCK}
+ROUND_HIST_BINS, ROUND_MOM = 1 << 20, 16
 
 
 class CloopsError(RuntimeError):
@@ -46,6 +47,8 @@ _SIGNATURES = {
     "cloops_range_counts": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "cloops_region_pets": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "cloops_pass_run": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, C.POINTER(_vp), _vp]),
+    "cloops_pass_run_stats": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, C.POINTER(_vp), _vp]),
+    "cloops_round_middle": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "cloops_pass_run_host": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, C.POINTER(_vp), _vp]),
     "cloops_pass_sizes": (C.c_int, [_vp, _vp, _vp]),
     "cloops_pass_device_ptr": (_vp, [_vp, C.c_int]),

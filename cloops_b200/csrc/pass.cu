@@ -19,6 +19,8 @@ int cluster_summary(const int32_t* d_x, const int32_t* d_y, const int32_t* d_lab
                     int32_t* d_size, uint8_t* d_kind, uint8_t* d_row_kind, cudaStream_t st);
 int row_kinds(const int32_t* d_labels, int64_t n, const uint8_t* d_kind, int64_t k, uint8_t* d_row_kind, cudaStream_t st);
 int coverage_build(const int32_t* d_x, const int32_t* d_y, int64_t n, cloops_coverage** out, cudaStream_t st);
+int pass_distance_stats(const int* xs, const int* ys, const unsigned char* member_kind, int n_members, const unsigned char* kind, int k,
+                        const int* raw_x, const int* raw_y, int n_raw, int cut, int* d_hist, double* d_mom, cudaStream_t st);
 int range_counts_dev(const cloops_coverage* cov, const int32_t* d_cand, int64_t ncand, const int* d_ncand, int32_t* d_out,
                      cudaStream_t st);
 }  // namespace cloops
@@ -102,7 +104,7 @@ static void pass_release(cloops_pass* p, cudaStream_t st) {
 }
 
 static int pass_run(cloops_pass* p, const int32_t* d_x, const int32_t* d_y, int64_t n, int32_t eps, int32_t minPts, int32_t cut,
-                    int32_t variant, int32_t score, cudaStream_t st) {
+                    int32_t variant, int32_t score, cudaStream_t st, int32_t* d_hist = nullptr, double* d_mom = nullptr) {
     p->n = (int)n;
     if (n == 0) return 0;
     RET_IF(pool_init());
@@ -141,6 +143,10 @@ static int pass_run(cloops_pass* p, const int32_t* d_x, const int32_t* d_y, int6
         if ((rc = cluster_summary(p->xs, p->ys, p->labels, p->n_members, k, p->bbox, p->size, p->kind, nullptr, st))) break;
         if ((rc = row_kinds(p->labels, p->n_members, p->kind, k, p->member_kind, st))) break;
         stage_mark("summary", st);
+        if (d_hist && d_mom) {
+            if ((rc = pass_distance_stats(p->xs, p->ys, p->member_kind, p->n_members, p->kind, k, d_x, d_y, (int)n, cut, d_hist, d_mom, st))) break;
+            stage_mark("distance_stats", st);
+        }
         if (score && k > 0) {
             Temp tmp(st);
             int *flag, *pos;
@@ -189,6 +195,26 @@ int cloops_pass_run(const int32_t* d_x, const int32_t* d_y, int64_t n, int32_t e
     stages_begin(st);
     cloops_pass* p = new cloops_pass();
     int rc = pass_run(p, d_x, d_y, n, eps, minPts, cut, variant, score, st);
+    if (rc != 0) {
+        pass_release(p, st);
+        return rc;
+    }
+    *out = p;
+    return stages_end(st);
+}
+
+int cloops_pass_run_stats(const int32_t* d_x, const int32_t* d_y, int64_t n, int32_t eps, int32_t minPts, int32_t cut, int32_t variant,
+                          int32_t score, int32_t* d_hist, double* d_mom, cloops_pass** out, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!out) return fail(CLOOPS_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (n < 0 || n > 0x7fffff00LL) return fail(CLOOPS_EINVAL, "n=%lld out of range", (long long)n);
+    if (minPts < 1) return fail(CLOOPS_EINVAL, "minPts must be >= 1 (got %d)", minPts);
+    if (variant != CLOOPS_V1 && variant != CLOOPS_V2 && variant != CLOOPS_BLOCK) return fail(CLOOPS_EINVAL, "unknown variant %d", variant);
+    if (!d_hist || !d_mom) return fail(CLOOPS_EINVAL, "round accumulators are NULL");
+    stages_begin(st);
+    cloops_pass* p = new cloops_pass();
+    int rc = pass_run(p, d_x, d_y, n, eps, minPts, cut, variant, score, st, d_hist, d_mom);
     if (rc != 0) {
         pass_release(p, st);
         return rc;

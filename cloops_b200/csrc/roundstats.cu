@@ -1,0 +1,151 @@
+// Distance statistics of one clustering round, reduced on the device (cLoops/pipe.py:59-63,106-109,120-127,259 and
+// cLoops/ests.py:36-61).  The reference pools two Python lists over all chromosomes -- dis: Y-X of the members of
+// inter-ligation clusters; dss: Y-X of the rows removed by the cut filter plus the members of self-ligation clusters --
+// and derives the next round's distance cut-off from the mean / std / median of their log2.  Here every chromosome adds
+// to one accumulator per round: (count, sum, sum of squares) of log2|d| in float64 and an exact histogram of the positive
+// self-ligation distances (the median is an order statistic; log2 is monotone).  Across GPUs the accumulators are
+// all-reduced (NCCL) -- 4 MB instead of the distance lists themselves.
+//
+// A chromosome without inter-ligation clusters contributes nothing, not even its dss (pipe.py:121-122): the kernels
+// read the chromosome's inter-ligation cluster count on the device and return early.
+#include "common.cuh"
+
+namespace cloops {
+
+#define RS_BINS CLOOPS_ROUND_HIST_BINS
+#define RS_LOCAL 4096            // distances below this are histogrammed in shared memory first (self-ligation lump)
+#define RS_GRID 592              // 4 CTAs per SM
+#define RS_NQ 8
+
+__global__ void __launch_bounds__(256) count_inter_kernel(const unsigned char* __restrict__ kind, int k, int* __restrict__ n_inter) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = __syncthreads_count(c < k && kind[c] == 1);
+    if (threadIdx.x == 0 && t) atomicAdd(n_inter, t);
+}
+
+// members: [n_members] (X, Y, kind) of the clustered PETs (index order, or row order for blockDBSCAN);
+// raw: [n_raw] the chromosome's rows, scanned for the ones the cut filter removed (signed Y-X < cut), only when cut > 0.
+__global__ void __launch_bounds__(256) dist_stats_kernel(const int* __restrict__ xs, const int* __restrict__ ys,
+                                                         const unsigned char* __restrict__ member_kind, int n_members,
+                                                         const int* __restrict__ raw_x, const int* __restrict__ raw_y, int n_raw, int cut,
+                                                         const int* __restrict__ n_inter, int* __restrict__ hist,
+                                                         double* __restrict__ partial) {
+    __shared__ int s_hist[RS_LOCAL];
+    __shared__ double s_red[8][RS_NQ];
+    if (*n_inter == 0) return;                                     // pipe.py:121-122
+    for (int t = threadIdx.x; t < RS_LOCAL; t += blockDim.x) s_hist[t] = 0;
+    __syncthreads();
+    double q[RS_NQ] = {0, 0, 0, 0, 0, 0, 0, 0};                    // n_i, S_i, Q_i, n_s, S_s, Q_s, raw_i, raw_s
+    const long long total = (long long)n_members + (cut > 0 ? n_raw : 0);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int d, which;                                              // which: 1 inter, 2 self, 0 neither
+        if (i < n_members) {
+            which = member_kind[i];
+            d = ys[i] - xs[i];
+        } else {
+            const long long j = i - n_members;
+            d = raw_y[j] - raw_x[j];
+            which = d < cut ? 2 : 0;
+        }
+        if (which == 0) continue;
+        const unsigned a = (unsigned)(d < 0 ? -d : d);              // ests.py:40-41 np.abs
+        const int o = which == 1 ? 0 : 3;
+        q[6 + (which == 1 ? 0 : 1)] += 1.0;
+        if (a == 0) continue;                                      // ests.py:44-45: zero distances are dropped
+        const double lg = log2((double)a);
+        q[o] += 1.0; q[o + 1] += lg; q[o + 2] += lg * lg;
+        if (which == 2) {
+            if (a < RS_LOCAL) atomicAdd(&s_hist[a], 1);
+            else atomicAdd(&hist[a < RS_BINS ? a : RS_BINS], 1);
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < RS_NQ; ++k) {
+        double v = q[k];
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+        if (lane == 0) s_red[warp][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < RS_NQ) {
+        double v = 0;
+        for (int w = 0; w < 8; ++w) v += s_red[w][threadIdx.x];    // fixed order: the sums are reproducible
+        partial[blockIdx.x * RS_NQ + threadIdx.x] = v;
+    }
+    for (int t = threadIdx.x; t < RS_LOCAL; t += blockDim.x)
+        if (s_hist[t]) atomicAdd(&hist[t], s_hist[t]);
+}
+
+// mom: 0 n_i, 1 S_i, 2 Q_i, 3 n_s, 4 S_s, 5 Q_s, 6 len(dis), 7 len(dss), 8 chromosomes with inter-ligation clusters
+__global__ void __launch_bounds__(32) dist_stats_commit_kernel(const double* __restrict__ partial, int nblocks, const int* __restrict__ n_inter,
+                                                               double* __restrict__ mom) {
+    if (*n_inter == 0) return;
+    const int k = threadIdx.x;
+    if (k < RS_NQ) {
+        double v = 0;
+        for (int b = 0; b < nblocks; ++b) v += partial[b * RS_NQ + k];
+        mom[k] += v;
+    }
+    if (k == RS_NQ) mom[8] += 1.0;
+}
+
+// the two middle order statistics of the histogrammed values: out[0] = value of rank (k-1)/2, out[1] = value of rank k/2
+// (0-based), k = mom[3]; -1 when k == 0, RS_BINS when the rank lies in the overflow bin
+__global__ void __launch_bounds__(1024) hist_middle_kernel(const int* __restrict__ hist, const double* __restrict__ mom, long long* __restrict__ out) {
+    __shared__ long long s_sum[1024];
+    const int per = (RS_BINS + 1 + 1023) / 1024;
+    const int b0 = threadIdx.x * per, b1 = min(b0 + per, RS_BINS + 1);
+    long long mine = 0;
+    for (int b = b0; b < b1; ++b) mine += hist[b];
+    s_sum[threadIdx.x] = mine;
+    __syncthreads();
+    const long long k = (long long)mom[3];
+    if (threadIdx.x == 0 && k == 0) { out[0] = -1; out[1] = -1; }
+    if (k == 0) return;
+    long long before = 0;
+    for (int t = 0; t < (int)threadIdx.x; ++t) before += s_sum[t];
+    for (int w = 0; w < 2; ++w) {
+        const long long r = w == 0 ? (k - 1) / 2 : k / 2;
+        if (r < before || r >= before + mine) continue;
+        long long acc = before;
+        for (int b = b0; b < b1; ++b) {
+            acc += hist[b];
+            if (r < acc) { out[w] = b; break; }
+        }
+    }
+}
+
+int pass_distance_stats(const int* xs, const int* ys, const unsigned char* member_kind, int n_members, const unsigned char* kind, int k,
+                        const int* raw_x, const int* raw_y, int n_raw, int cut, int* d_hist, double* d_mom, cudaStream_t st) {
+    Temp tmp(st);
+    int* d_ninter;
+    double* d_partial;
+    RET_IF(tmp.alloc(&d_ninter, 1));
+    RET_IF(tmp.alloc(&d_partial, (size_t)RS_GRID * RS_NQ));
+    CU_TRY(cudaMemsetAsync(d_ninter, 0, sizeof(int), st));
+    if (k > 0) LAUNCH(count_inter_kernel, cdiv(k, 256), 256, 0, st, kind, k, d_ninter);
+    LAUNCH(dist_stats_kernel, RS_GRID, 256, 0, st, xs, ys, member_kind, n_members, raw_x, raw_y, n_raw, cut, d_ninter, d_hist, d_partial);
+    LAUNCH(dist_stats_commit_kernel, 1, 32, 0, st, d_partial, RS_GRID, d_ninter, d_mom);
+    return 0;
+}
+
+}  // namespace cloops
+
+using namespace cloops;
+
+extern "C" int cloops_round_middle(const int32_t* d_hist, const double* d_mom, int64_t* h_middle, double* h_mom, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!d_hist || !d_mom || !h_middle || !h_mom) return fail(CLOOPS_EINVAL, "NULL argument");
+    RET_IF(pool_init());
+    Temp tmp(st);
+    long long* d_out;
+    RET_IF(tmp.alloc(&d_out, 2));
+    LAUNCH(hist_middle_kernel, 1, 1024, 0, st, d_hist, d_mom, d_out);
+    long long out[2];
+    CU_TRY(cudaMemcpyAsync(out, d_out, sizeof(out), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(h_mom, d_mom, CLOOPS_ROUND_MOM * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    h_middle[0] = out[0];
+    h_middle[1] = out[1];
+    return 0;
+}

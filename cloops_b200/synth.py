@@ -48,11 +48,30 @@ def config2(n: int = 10_000_000, seed: int = 20240 + 200):
     return chromosome(n, 249_000_000, seed, loop_frac=0.08, sigma=500.0)
 
 
-def genome(n_total: int, config: int, sigma: float = 1500.0, loop_frac: float = 0.06):
-    """Per-chromosome sets with PET counts proportional to hg38 lengths (configs 3 and 4)."""
+GENOME_PARAMS = {3: dict(sigma=1500.0, loop_frac=0.06), 4: dict(sigma=1500.0, loop_frac=0.06)}
+
+
+def genome_counts(n_total: int):
+    """PETs per chromosome, proportional to the hg38 lengths (configs 3 and 4)."""
     tot = float(sum(HG38))
-    out = []
-    for ci, (name, L) in enumerate(zip(CHROMS, HG38)):
-        n = int(round(n_total * L / tot))
-        out.append((name, *chromosome(n, L, 20240 + config * 100 + ci, loop_frac=loop_frac, sigma=sigma)))
-    return out
+    return [int(round(n_total * L / tot)) for L in HG38]
+
+
+def genome_chrom(n_total: int, config: int, ci: int, sigma: float = 1500.0, loop_frac: float = 0.06):
+    """Chromosome ``ci`` (0-based, chr1..22, X) of the ``n_total``-PET genome of config 3 / 4: (name, X, Y)."""
+    n = genome_counts(n_total)[ci]
+    return (CHROMS[ci], *chromosome(n, HG38[ci], 20240 + config * 100 + ci, loop_frac=loop_frac, sigma=sigma))
+
+
+def genome(n_total: int, config: int, sigma: float = 1500.0, loop_frac: float = 0.06, only=None):
+    """Per-chromosome sets with PET counts proportional to hg38 lengths (configs 3 and 4); ``only``: the chromosome
+    indices wanted (a rank's shard)."""
+    return [genome_chrom(n_total, config, ci, sigma, loop_frac) for ci in range(len(HG38)) if only is None or ci in only]
+
+HIC_PETS_PER_KB = 66.0     # config 4: chr1 holds 16.4 M of the 200 M PETs on 249 Mb
+
+
+def hic_density(n: int, seed: int, sigma: float = 1500.0, loop_frac: float = 0.06):
+    """A chromosome of ``n`` PETs at the PET density of config 4 (deep Hi-C): length = n / 66 PETs per kb."""
+    length = int(n * 1000.0 / HIC_PETS_PER_KB)
+    return chromosome(n, length, seed, loop_frac=loop_frac, sigma=sigma)

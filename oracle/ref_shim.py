@@ -8,7 +8,9 @@ is copied into this repository.
 
 It exists for ONE purpose: to generate and re-check the golden vectors under ``tests/golden/``
 (``oracle/make_golden.py``) and to pin ``oracle/spec.py``. ``/root/reference`` does not exist on
-the GPU box, so nothing in ``-m gpu`` tests, ``smoke()`` or ``bench.py`` imports this file.
+the GPU box; there the loader falls back to ``oracle/_ref`` (an unmodified copy made by ``oracle/make_ref.py``, git-ignored,
+shipped with the gpurun snapshot), which is what ``bench.py --impl reference`` / ``cpu_baseline`` time and what the drop-in
+test runs.  The product (``cloops_b200/``) never imports this file.
 """
 from __future__ import annotations
 
@@ -16,7 +18,22 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("CLOOPS_REFERENCE", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root() -> str:
+    """CLOOPS_REFERENCE, else the mounted reference tree, else the copy made by oracle/make_ref.py (git-ignored,
+    shipped to the GPU box by gpurun)."""
+    env = os.environ.get("CLOOPS_REFERENCE")
+    if env:
+        return env
+    for cand in ("/root/reference", os.path.join(_HERE, "_ref")):
+        if os.path.isfile(os.path.join(cand, "cLoops", "cDBSCAN2.py")):
+            return cand
+    return "/root/reference"
+
+
+REF_ROOT = _find_root()
 
 
 def available() -> bool:
