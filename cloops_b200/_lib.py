@@ -45,6 +45,7 @@ _SIGNATURES = {
     "cloops_coverage_free": (None, [_vp]),
     "cloops_coverage_release": (None, [_vp, _vp]),
     "cloops_range_counts": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    "cloops_range_work": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp]),
     "cloops_region_pets": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "cloops_pass_run": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, C.POINTER(_vp), _vp]),
     "cloops_pass_run_stats": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, C.POINTER(_vp), _vp]),
@@ -53,6 +54,7 @@ _SIGNATURES = {
     "cloops_pass_sizes": (C.c_int, [_vp, _vp, _vp]),
     "cloops_pass_device_ptr": (_vp, [_vp, C.c_int]),
     "cloops_pass_fetch": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "cloops_pass_fetch_records": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "cloops_pass_free": (None, [_vp, _vp]),
 }
 

@@ -59,8 +59,19 @@ class CoverageModel:
         return 2
 
 
+#: set by pipe.py: f -> the chromosome object already resident in HBM (key, X, Y, dx, dy), or None
+RESIDENT = None
+
+
 def getGenomeCoverage(f, cut=0):
     """cModel.py:45-57: ``(model, N)``; ``(None, 0)`` when fewer than 2 PETs survive ``cut``."""
+    ch = RESIDENT(f) if (RESIDENT is not None and cut == 0) else None
+    if ch is not None:                                   # pipe(): the chromosome is in HBM already, discut is 0 (pipe.py:284)
+        if ch.n < 2:
+            return None, 0
+        m = CoverageModel(ch.X, ch.Y)
+        m._gpu = device.Coverage(ch.dx, ch.dy)
+        return m, ch.n
     key, mat = parseJd(f, cut)
     if mat.shape[0] < 2:
         return None, 0
@@ -250,32 +261,55 @@ def removeDup(ds, bpcut=1e-5):
     return uniqueds
 
 
-def getIntSig(f, records, minPts, discut):
-    """cModel.py:262-331.  All candidates of the chromosome are counted in ONE batched kernel launch;
-    filtering (:284-291), key numbering (:280,292), de-duplication and Bonferroni follow the reference."""
+def countCandidates(f, records, minPts, discut):
+    """The GPU half of getIntSig (cModel.py:262-295): coverage model, (ra, rb, rab) of every candidate, the rab / distance
+    filters (:284-291) and the 123 permuted-background integers of the survivors.
+    -> None (no model: fewer than 2 PETs) or dict(N, names, cand, keep, dist, counts)."""
     print("Starting estimate significance for %s candidate interactions in %s" % (len(records), f))
     model, N = getGenomeCoverage(f, discut)
     print("Genomic coverage model built from %s" % f)
     if N == 0:
         print("No cis-PETs parsed as requiring distance cutoff >%s from %s" % (discut, f))
         return None
-    cand = np.array([[max(0, r[1]), r[2], max(0, r[4]), r[5]] for r in records], dtype=np.int64).reshape(-1, 4)
-    counts = model.gpu.range_counts(cand) if len(cand) else np.zeros((0, 123), np.int32)
+    if isinstance(records, np.ndarray):                  # pipe(): int array [K,4] = minX, maxX, minY, maxY
+        cand = records.astype(np.int64).reshape(-1, 4)
+        names = tuple(os.path.split(f)[1].replace("mem:", "").replace(".jd", "").split("-")[:2])
+    else:
+        cand = np.array([[r[1], r[2], r[4], r[5]] for r in records], dtype=np.int64).reshape(-1, 4)
+        names = (records[0][0], records[0][3]) if len(records) else ("", "")
+    cand[:, 0] = np.maximum(cand[:, 0], 0)               # cModel.py:281-282
+    cand[:, 2] = np.maximum(cand[:, 2], 0)
     need = max(minPts)
     dist_all = np.abs((cand[:, 2] + cand[:, 3]) / 2.0 - (cand[:, 0] + cand[:, 1]) / 2.0) if len(cand) else np.zeros(0)
-    keep = np.flatnonzero((dist_all >= discut) & (counts[:, 2] >= need)) if len(cand) else np.zeros(0, np.int64)
+    # two launches, as the reference's two steps: (ra, rb, rab) of every candidate (getPETsforRegions, :287), then the 123
+    # integers of the permuted background only for the candidates that pass rab >= max(minPts) (:290-295)
+    keep = np.zeros(0, np.int64)
+    counts = np.zeros((0, 123), np.int32)
+    if len(cand):
+        rab = model.gpu.region_pets(cand)[:, 2]
+        keep = np.flatnonzero((dist_all >= discut) & (rab >= need))
+        if len(keep):
+            counts = model.gpu.range_counts(cand[keep])
+    model.gpu.close()
+    return {"N": N, "names": names, "cand": cand, "keep": keep, "dist": dist_all, "counts": counts}
+
+
+def tableFromCounts(c):
+    """The host half of getIntSig (cModel.py:295-331): the reference's numpy / scipy statistics on the counted integers,
+    key numbering (:280,292), removeDup twice (:318,322), Bonferroni (:327-330).  -> DataFrame or None."""
+    if c is None:
+        return None
+    N, (chrom_a, chrom_b), cand, keep, dist_all, counts = c["N"], c["names"], c["cand"], c["keep"], c["dist"], c["counts"]
     ds = {}
     if len(keep):
-        ra, rb, rab, es, fdr, hyp, pop, nbp = _stats_batch(counts[keep], N)
+        ra, rb, rab, es, fdr, hyp, pop, nbp = _stats_batch(counts, N)
+        chrom = chrom_a
         for i, k in enumerate(keep.tolist()):                  # key number = accepted so far (cModel.py:280,292)
-            r = records[k]
-            chrom = r[0]
-            ds["%s-%s-%s" % (r[0], r[3], i)] = {
+            ds["%s-%s-%s" % (chrom_a, chrom_b, i)] = {
                 "distance": float(dist_all[k]), "ra": int(ra[i]), "rb": int(rb[i]), "rab": int(rab[i]), "ES": es[i], "FDR": fdr[i],
                 "hypergeometric_p-value": hyp[i], "poisson_p-value": pop[i], "binomial_p-value": nbp[i],
                 "iva": "%s:%s-%s" % (chrom, int(cand[k, 0]), int(cand[k, 1])), "ivb": "%s:%s-%s" % (chrom, int(cand[k, 2]), int(cand[k, 3])),
             }
-    del model
     if len(ds) == 0:
         return None
     ds = removeDup(ds)
@@ -289,6 +323,12 @@ def getIntSig(f, records, minPts, discut):
     ds["binomial_p-value_corrected"] = getBonPvalues(ds["binomial_p-value"])
     ds["hypergeometric_p-value_corrected"] = getBonPvalues(ds["hypergeometric_p-value"])
     return ds
+
+
+def getIntSig(f, records, minPts, discut):
+    """cModel.py:262-331.  All candidates of the chromosome are counted in batched kernel launches; filtering (:284-291),
+    key numbering (:280,292), de-duplication and Bonferroni follow the reference."""
+    return tableFromCounts(countCandidates(f, records, minPts, discut))
 
 
 def markIntSig(ds, escut=2.0, fdrcut=1e-2, bpcut=1e-3, ppcut=1e-5, hypcut=1e-10):

@@ -177,6 +177,35 @@ __global__ void __launch_bounds__(32 * RC_WARPS) range_count_kernel(const int* _
     for (int t = lane; t < NOUT; t += 32) out[m * NOUT + t] = acc[t];
 }
 
+// Algorithmic work of range_count_kernel for a candidate list: PETs with X inside the hull of all windows and
+// PETs with Y inside it, summed over the candidates -- out[0], out[1].  Exact slices (not the 256-bp bucket slices the
+// count kernel cuts): per hull interval, #{c : lo <= c <= hi} = #{bucket < b(hi)} - #{bucket < b(lo)} corrected by an exact
+// scan of the two boundary buckets.
+__device__ __forceinline__ int exact_rank(const int* __restrict__ a, int n, int v, bool upper) {
+    // number of entries < v (upper = false) or <= v (upper = true) in an array sorted by bucket only
+    int lo = lower_bound_i(a, n, v), hi = upper_bound_i(a, n, v);
+    int r = lo;
+    for (int j = lo; j < hi; ++j) r += upper ? (__ldg(a + j) <= v) : (__ldg(a + j) < v);
+    return r;
+}
+__global__ void __launch_bounds__(128) range_work_kernel(const int* __restrict__ xs_x, const int* __restrict__ ys_y, int n,
+                                                         const int* __restrict__ cand, long long ncand, int win,
+                                                         unsigned long long* __restrict__ out) {
+    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long vx = 0, vy = 0;
+    if (m < ncand) {
+        Windows W;
+        const int4 c = __ldg(reinterpret_cast<const int4*>(cand) + m);
+        make_windows(c.x, c.y, c.z, c.w, win, W);
+        for (int h = 0; h < W.nh; ++h) {
+            vx += (unsigned long long)max(0, exact_rank(xs_x, n, W.h1[h], true) - exact_rank(xs_x, n, W.h0[h], false));
+            vy += (unsigned long long)max(0, exact_rank(ys_y, n, W.h1[h], true) - exact_rank(ys_y, n, W.h0[h], false));
+        }
+    }
+    for (int d = 16; d > 0; d >>= 1) { vx += __shfl_down_sync(0xffffffffu, vx, d); vy += __shfl_down_sync(0xffffffffu, vy, d); }
+    if ((threadIdx.x & 31) == 0 && (vx | vy)) { atomicAdd(out, vx); atomicAdd(out + 1, vy); }
+}
+
 }  // namespace cloops
 
 using namespace cloops;
@@ -254,6 +283,26 @@ int cloops_range_counts(const cloops_coverage* cov, const int32_t* d_cand, int64
     }
     stage_mark("range_counts", st);
     return stages_end(st);
+}
+
+/* Measurement aid (bench.py roofline of the range-count kernel): h_work[0] = sum over candidates of PETs with X
+ * inside the hull of the candidate's windows, h_work[1] = same for Y; win = 5 (range_counts) or 0 (region_pets).  Synchronises. */
+int cloops_range_work(const cloops_coverage* cov, const int32_t* d_cand, int64_t m, int32_t win, uint64_t* h_work, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!cov || !h_work) return fail(CLOOPS_EINVAL, "NULL argument");
+    h_work[0] = h_work[1] = 0;
+    if (m <= 0 || cov->n == 0) return 0;
+    Temp tmp(st);
+    unsigned long long* d_w;
+    RET_IF(tmp.alloc(&d_w, 2));
+    CU_TRY(cudaMemsetAsync(d_w, 0, 2 * sizeof(unsigned long long), st));
+    LAUNCH(range_work_kernel, (unsigned)((m + 127) / 128), 128, 0, st, cov->xs_x, cov->ys_y, cov->n, d_cand, (long long)m, (int)win, d_w);
+    unsigned long long w[2];
+    CU_TRY(cudaMemcpyAsync(w, d_w, sizeof(w), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    h_work[0] = w[0];
+    h_work[1] = w[1];
+    return 0;
 }
 
 int cloops_region_pets(const cloops_coverage* cov, const int32_t* d_cand, int64_t m, int32_t* d_out, void* stream) {

@@ -273,8 +273,7 @@ const void* cloops_pass_device_ptr(const cloops_pass* p, int which) {
 }
 
 /* Copies results to HOST buffers (any may be NULL) and synchronises the stream once:
- * h_bbox int32[k,4], h_kind u8[k], h_member_kind u8[n_members], h_member_dist int32[n_members] (Y - X of each member,
- * index order), h_counts int32[m,123]. */
+ * h_bbox int32[k,4], h_kind u8[k], h_member_kind u8[n_members], h_counts int32[m,123]. */
 int cloops_pass_fetch(const cloops_pass* p, int32_t* h_bbox, uint8_t* h_kind, uint8_t* h_member_kind, int32_t* h_counts, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (!p) return fail(CLOOPS_EINVAL, "pass is NULL");
@@ -282,6 +281,18 @@ int cloops_pass_fetch(const cloops_pass* p, int32_t* h_bbox, uint8_t* h_kind, ui
     if (h_kind && p->k) CU_TRY(cudaMemcpyAsync(h_kind, p->kind, (size_t)p->k, cudaMemcpyDeviceToHost, st));
     if (h_member_kind && p->n_members) CU_TRY(cudaMemcpyAsync(h_member_kind, p->member_kind, (size_t)p->n_members, cudaMemcpyDeviceToHost, st));
     if (h_counts && p->scored && p->m) CU_TRY(cudaMemcpyAsync(h_counts, p->counts, (size_t)p->m * 123 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+/* Candidate-record view of a pass for the host (pipe.py:76-102): h_bbox int32[k,4], h_size int32[k], h_kind u8[k]
+ * (any may be NULL); one synchronisation. */
+int cloops_pass_fetch_records(const cloops_pass* p, int32_t* h_bbox, int32_t* h_size, uint8_t* h_kind, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!p) return fail(CLOOPS_EINVAL, "pass is NULL");
+    if (h_bbox && p->k) CU_TRY(cudaMemcpyAsync(h_bbox, p->bbox, (size_t)p->k * 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (h_size && p->k) CU_TRY(cudaMemcpyAsync(h_size, p->size, (size_t)p->k * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (h_kind && p->k) CU_TRY(cudaMemcpyAsync(h_kind, p->kind, (size_t)p->k, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
     return 0;
 }

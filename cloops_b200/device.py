@@ -13,6 +13,33 @@ COORD_LIMIT = 1 << 30
 INFO_KEYS = ("n_active", "n_clusters", "n_components", "n_core", "n_dead", "n_strips", "key_bits", "n_labelled")
 
 
+class Profile:
+    """Measurement hooks (bench.py): with ``Profile.on`` the C library times its stages with CUDA events (one extra
+    synchronisation per call) and the wrappers below add them up, together with the algorithmic bytes SURVEY 8d defines
+    for the two graded kernels.  ``d2h_bytes`` is counted always (e2e accounting)."""
+    on = False
+    stages: dict = {}
+    rq_bytes = 0          # region query: 12 B per active PET per launch
+    rc_bytes = 0          # range counts: 8 B per PET in the hull slices + 4 B per output integer
+    d2h_bytes = 0
+
+    @classmethod
+    def begin(cls):
+        cls.on, cls.stages, cls.rq_bytes, cls.rc_bytes = True, {}, 0, 0
+        _lib.lib().cloops_set_profiling(1)
+
+    @classmethod
+    def end(cls):
+        cls.on = False
+        _lib.lib().cloops_set_profiling(0)
+        return dict(cls.stages)
+
+    @classmethod
+    def add_stages(cls):
+        for k, v in _lib.stage_times().items():
+            cls.stages[k] = cls.stages.get(k, 0.0) + v
+
+
 def require_cuda() -> torch.device:
     if not torch.cuda.is_available():
         raise CloopsError("cloops_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
@@ -185,7 +212,16 @@ class Coverage:
         m = d.shape[0]
         out = torch.empty((max(m, 1), 123), dtype=torch.int32, device=self.device)
         check(_lib.lib().cloops_range_counts(self._h, d.data_ptr(), m, out.data_ptr(), _stream()))
+        self._profile(d, m, 5, 123)
+        Profile.d2h_bytes += m * 123 * 4
         return out[:m].cpu().numpy()
+
+    def _profile(self, d, m, win, nout):
+        if Profile.on and m:
+            Profile.add_stages()
+            work = (C.c_uint64 * 2)()
+            check(_lib.lib().cloops_range_work(self._h, d.data_ptr(), m, win, C.addressof(work), _stream()))
+            Profile.rc_bytes += 8 * (int(work[0]) + int(work[1])) + 4 * nout * m
 
     def region_pets(self, cand) -> np.ndarray:
         """cand [m,4] -> int32 [m,3] = ra, rb, rab (getPETsforRegions, cModel.py:72-80)."""
@@ -193,6 +229,8 @@ class Coverage:
         m = d.shape[0]
         out = torch.empty((max(m, 1), 3), dtype=torch.int32, device=self.device)
         check(_lib.lib().cloops_region_pets(self._h, d.data_ptr(), m, out.data_ptr(), _stream()))
+        self._profile(d, m, 0, 3)
+        Profile.d2h_bytes += m * 3 * 4
         return out[:m].cpu().numpy()
 
     def close(self):
@@ -223,19 +261,32 @@ class Pass:
     _WHICH = {"bbox": (0, "<i4"), "size": (1, "<i4"), "kind": (2, "|u1"), "xs": (3, "<i4"), "ys": (4, "<i4"),
               "labels_sorted": (5, "<i4"), "member_kind": (6, "|u1"), "cand": (7, "<i4"), "counts": (8, "<i4")}
 
-    def __init__(self, x, y, eps: int, minPts: int, variant: int = _lib.V2, cut: int = 0, score: bool = True, host: bool = False):
+    def __init__(self, x, y, eps: int, minPts: int, variant: int = _lib.V2, cut: int = 0, score: bool = True, host: bool = False,
+                 stats=None):
+        """``stats`` = (hist int32 CUDA tensor [ROUND_HIST_BINS + 1], mom float64 CUDA tensor [ROUND_MOM]): the round's distance
+        accumulators this chromosome adds to (cloops_pass_run_stats)."""
         require_cuda()
-        self._keep = (x, y)
+        self._keep = (x, y, stats)
         n = x.numel()
         h = C.c_void_p()
-        fn = _lib.lib().cloops_pass_run_host if host else _lib.lib().cloops_pass_run
-        check(fn(x.data_ptr(), y.data_ptr(), n, int(eps), int(minPts), int(cut), int(variant), 1 if score else 0, C.byref(h), _stream()))
+        args = (x.data_ptr(), y.data_ptr(), n, int(eps), int(minPts), int(cut), int(variant), 1 if score else 0)
+        if stats is not None:
+            if host:
+                raise CloopsError("round statistics need device-resident coordinates")
+            check(_lib.lib().cloops_pass_run_stats(*args, stats[0].data_ptr(), stats[1].data_ptr(), C.byref(h), _stream()))
+        else:
+            fn = _lib.lib().cloops_pass_run_host if host else _lib.lib().cloops_pass_run
+            check(fn(*args, C.byref(h), _stream()))
         self._h = h
         sizes, info = (C.c_int64 * 6)(), (C.c_int64 * 8)()
         check(_lib.lib().cloops_pass_sizes(h, C.addressof(sizes), C.addressof(info)))
         self.n_members, self.n_clusters, self.n_candidates, self.scored, self.n_rows = (int(v) for v in sizes[:5])
         self.info = dict(zip(INFO_KEYS, (int(v) for v in info)))
         self._dev = torch.device("cuda", torch.cuda.current_device())
+        if Profile.on:
+            Profile.add_stages()
+            if variant != _lib.BLOCK:
+                Profile.rq_bytes += 12 * self.info["n_active"]
 
     def _view(self, name: str) -> torch.Tensor:
         which, typestr = self._WHICH[name]
@@ -261,6 +312,15 @@ class Pass:
         """D2H copies into (pinned) host tensors, one synchronisation."""
         ptr = lambda t: t.data_ptr() if t is not None else None
         check(_lib.lib().cloops_pass_fetch(self._h, ptr(h_bbox), ptr(h_kind), ptr(h_member_kind), ptr(h_counts), _stream()))
+
+    def records(self):
+        """Host copies (numpy) of bbox int32[k,4], size int32[k], kind u8[k]; one synchronisation."""
+        k = self.n_clusters
+        bbox, size, kind = np.empty((k, 4), np.int32), np.empty(k, np.int32), np.empty(k, np.uint8)
+        if k:
+            check(_lib.lib().cloops_pass_fetch_records(self._h, bbox.ctypes.data, size.ctypes.data, kind.ctypes.data, _stream()))
+        Profile.d2h_bytes += k * 21
+        return bbox, size, kind
 
     def close(self):
         if getattr(self, "_h", None):

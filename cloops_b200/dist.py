@@ -100,6 +100,24 @@ def all_gather_concat(t):
     return torch.cat([b[:k] for b, k in zip(bufs, sizes)])
 
 
+def all_reduce_sum(t):
+    """In-place sum over ranks of a tensor (NCCL for CUDA tensors, gloo for CPU tensors)."""
+    if world() > 1:
+        import torch.distributed as td
+        td.all_reduce(t, op=td.ReduceOp.SUM)
+    return t
+
+
+def all_gather_objects(obj):
+    """-> [object of rank 0, ..., object of rank world-1] on every rank."""
+    if world() == 1:
+        return [obj]
+    import torch.distributed as td
+    out = [None] * world()
+    td.all_gather_object(out, obj)
+    return out
+
+
 def broadcast_object(obj, src: int = 0):
     if world() == 1:
         return obj

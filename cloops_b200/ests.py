@@ -70,3 +70,24 @@ def cut_from_moments(inter_parts, self_parts, self_sorted_distances):
     cut1 = med + 3 * ss
     cut2 = (ms * ss + mi * si) / (ss + si)
     return int(2 ** min([cut1, cut2])), int(2 ** med)
+
+
+def cut_from_round(mom, lo, hi, guard=1e-9):
+    """estIntSelCutFrag (cLoops/ests.py:36-61) from a round's device-reduced statistics: ``mom`` = n, sum, sum of squares of
+    log2|d| of the inter-ligation (0..2) and self-ligation (3..5) distances, ``lo`` / ``hi`` = the two middle order statistics
+    of the positive self-ligation distances.  -> integer cut-off, or None when the estimate must be redone from the pooled
+    distances: a middle value outside the histogram (1 <= d < 2^20), or 2**cut within ``guard`` (relative) of an integer, where
+    the summation order of the moments could flip ``int()``."""
+    ni, si, qi, ns, ss, qs = mom[:6]
+    if ni <= 0 or ns <= 0 or lo < 1 or hi < 1 or lo >= (1 << 20) or hi >= (1 << 20):
+        return None
+    mi, ms = si / ni, ss / ns
+    sdi = float(np.sqrt(max(qi / ni - mi * mi, 0.0)))
+    sds = float(np.sqrt(max(qs / ns - ms * ms, 0.0)))
+    med = (float(np.log2(float(lo))) + float(np.log2(float(hi)))) / 2.0 if lo != hi else float(np.log2(float(lo)))
+    cut1 = med + 3 * sds
+    cut2 = (ms * sds + mi * sdi) / (sds + sdi)
+    c = 2 ** min([cut1, cut2])
+    if not np.isfinite(c) or abs(c - round(c)) <= guard * max(1.0, c):
+        return None
+    return int(c)

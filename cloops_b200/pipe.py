@@ -17,12 +17,20 @@ import numpy as np
 import pandas as pd
 
 from . import _lib, device, dist
+from . import cModel
 from .cModel import getIntSig, markIntSig, markIntSigHic
-from .ests import cut_from_moments, estFragSize, estIntSelCutFrag
+from .ests import cut_from_round, estFragSize, estIntSelCutFrag
 from .io import loops2juice, loops2washU, parseJd, parseRawBedpe, parseRawBedpe2
 from .utils import getLogger, mainHelp
 
 logger = None
+
+
+def _resident_model(f):
+    """cModel.getGenomeCoverage hook: the chromosome already resident in HBM (discut = 0), instead of a second parse + upload."""
+    hit = _Resident._cache.get(f if f.startswith("mem:") else os.path.abspath(f))
+    return hit[1] if hit is not None else None
+
 
 #: which clusterer ``singleDBSCAN`` runs: the reference binds cDBSCAN2 (pipe.py:42) and keeps
 #: blockDBSCAN as a commented alternative (pipe.py:43)
@@ -30,30 +38,65 @@ DBSCAN_VARIANT = _lib.V2
 
 
 class _Resident:
-    """One chromosome's PETs on the host and in HBM, loaded once per .jd path."""
+    """One chromosome's PETs on the host and in HBM, loaded once per .jd path -- or registered from arrays under a
+    pseudo path (``_Resident.register``), which is how bench.py and the tests feed synthetic chromosomes without files."""
     _cache: dict = {}
 
-    def __init__(self, f):
-        self.key, mat = parseJd(f, cut=0)
-        self.ids = np.ascontiguousarray(mat[:, 0]) if len(mat) else np.zeros(0, np.int64)
-        self.X = np.ascontiguousarray(mat[:, 1]) if len(mat) else np.zeros(0, np.int64)
-        self.Y = np.ascontiguousarray(mat[:, 2]) if len(mat) else np.zeros(0, np.int64)
-        self.dx = device.to_device_i32(self.X, "X")
-        self.dy = device.to_device_i32(self.Y, "Y")
+    def __init__(self, f=None, key=None, X=None, Y=None, ids=None, dx=None, dy=None):
+        if f is not None:
+            self.key, mat = parseJd(f, cut=0)
+            ids = np.ascontiguousarray(mat[:, 0]) if len(mat) else np.zeros(0, np.int64)
+            X = np.ascontiguousarray(mat[:, 1]) if len(mat) else np.zeros(0, np.int64)
+            Y = np.ascontiguousarray(mat[:, 2]) if len(mat) else np.zeros(0, np.int64)
+        else:
+            self.key = tuple(key)
+        self.ids, self.X, self.Y = ids, X, Y
+        self.n = len(X)
+        self.dx = device.to_device_i32(X, "X") if dx is None else dx
+        self.dy = device.to_device_i32(Y, "Y") if dy is None else dy
 
     @classmethod
     def get(cls, f):
+        hit = cls._cache.get(f if f.startswith("mem:") else os.path.abspath(f))
+        if hit is not None and hit[0] is None:
+            return hit[1]
         st = os.stat(f)
         tag = (os.path.abspath(f), st.st_mtime_ns, st.st_size)
-        hit = cls._cache.get(tag[0])
         if hit is None or hit[0] != tag:
             hit = (tag, cls(f))
+            cls._cache.pop(tag[0], None)
             cls._cache[tag[0]] = hit
+            cls._evict(keep=tag[0])
         return hit[1]
+
+    #: file-backed chromosomes kept resident: at most this many bytes of coordinates in HBM (least recently loaded go first),
+    #: so direct callers of singleDBSCAN / runDBSCAN do not accumulate device memory; pipe() clears the cache when it is done
+    BUDGET_BYTES = int(os.environ.get("CLOOPS_RESIDENT_BYTES", str(48 << 30)))
+
+    @classmethod
+    def _evict(cls, keep):
+        total = sum(v[1].n * 8 for v in cls._cache.values())
+        for name in list(cls._cache):
+            if total <= cls.BUDGET_BYTES:
+                break
+            if name == keep or cls._cache[name][0] is None:          # registered arrays belong to their owner
+                continue
+            total -= cls._cache.pop(name)[1].n * 8
+
+    @classmethod
+    def register(cls, name, X, Y, dx=None, dy=None):
+        """A chromosome given as host arrays (and, optionally, its int32 CUDA tensors already in HBM) -> pseudo path
+        ``mem:<name>-<name>.jd``."""
+        f = "mem:%s-%s.jd" % (name, name)
+        cls._cache[f] = (None, cls(None, (name, name), X, Y, None, dx, dy))
+        return f
 
     @classmethod
     def clear(cls):
         cls._cache.clear()
+
+
+cModel.RESIDENT = _resident_model
 
 
 def _single(f, eps, minPts, cut=0):
@@ -91,101 +134,143 @@ def _single(f, eps, minPts, cut=0):
     return key, f, dataI, dataS, dis, (np.concatenate(dss) if dss else np.zeros(0, np.float64))
 
 
-def _moments(vals):
-    """(n, mean, M2) of log2(vals) in float64 on the device; vals: positive int32 CUDA tensor."""
-    import torch
-    n = int(vals.numel())
-    if n == 0:
-        return (0, 0.0, 0.0)
-    x = torch.log2(vals.to(torch.float64))
-    mean = x.mean()
-    return (n, float(mean), float(((x - mean) ** 2).sum()))
+class _RoundAcc:
+    """Device accumulators of one clustering round: exact histogram of the positive self-ligation distances and the
+    log2 moments of both distance collections (``cloops_pass_run_stats``, csrc/roundstats.cu).  They replace the pooled
+    ``dis`` / ``dss`` lists of cLoops/pipe.py:120-127; across GPUs they are summed with one all-reduce per round."""
+    _per_device: dict = {}
+
+    def __init__(self, dev):
+        import torch
+        self.hist = torch.zeros(_lib.ROUND_HIST_BINS + 1, dtype=torch.int32, device=dev)
+        self.mom = torch.zeros(_lib.ROUND_MOM, dtype=torch.float64, device=dev)
+
+    @classmethod
+    def get(cls):
+        dev = device.require_cuda()
+        if dev not in cls._per_device:
+            cls._per_device[dev] = cls(dev)
+        return cls._per_device[dev]
+
+    def reset(self):
+        self.hist.zero_()
+        self.mom.zero_()
+
+    def reduce(self):
+        dist.all_reduce_sum(self.hist)
+        dist.all_reduce_sum(self.mom)
+
+    def middle(self):
+        """-> (lo, hi, mom): the two middle order statistics of the self-ligation distances and the moments (host)."""
+        import ctypes as C
+        import torch
+        mid, mom = (C.c_int64 * 2)(), (C.c_double * _lib.ROUND_MOM)()
+        _lib.check(_lib.lib().cloops_round_middle(self.hist.data_ptr(), self.mom.data_ptr(), C.addressof(mid), C.addressof(mom),
+                                                  torch.cuda.current_stream().cuda_stream))
+        return int(mid[0]), int(mid[1]), [float(v) for v in mom]
 
 
-def _single_stats(f, eps, minPts, cut=0):
-    """As _single, but the distance collections stay in HBM: returns the candidate records, the raw
-    sizes of dis / dss, their log2 moments and the positive self-ligation distances (device tensor)."""
-    import torch
+def _weights(fs):
+    """PETs per chromosome file (LPT packing of chromosomes onto ranks, dist.assign): a .jd holds 24 B per PET."""
+    out = []
+    for f in fs:
+        hit = _Resident._cache.get(f)
+        out.append(hit[1].n * 24 if hit is not None else (os.path.getsize(f) if os.path.exists(f) else 1))
+    return out
+
+
+def _cluster_chrom(f, eps, minPts, cut, acc):
+    """One chromosome of one round on the GPU: cut filter (pipe.py:59-63), clusterer (:70), per-cluster records (:76-102)
+    and this chromosome's share of the round's distance statistics (:106-109), in ONE C-ABI call.
+    -> (key, inter-ligation records int32 [K,4] = minX, maxX, minY, maxY in ascending cluster id, #self-ligation clusters)"""
     ch = _Resident.get(f)
     key = ch.key
-    dataI, dataS = [], []
-    dd = ch.dy - ch.dx                                   # Y - X on the device
-    empty = torch.zeros(0, dtype=torch.int32, device=dd.device)
-    removed = dd[dd < cut] if cut > 0 else empty
-    n_act = int(dd.numel() - removed.numel())
-    if n_act == 0:
-        pos = removed.abs()
-        pos = pos[pos > 0]
-        return key, f, dataI, dataS, 0, int(removed.numel()), (0, 0.0, 0.0), _moments(pos), pos
+    empty = np.zeros((0, 4), np.int32)
+    if ch.n == 0:
+        return key, empty, 0
     sys.stderr.write("Clustering %s and %s using eps as %s, minPts as %s,pre-set distance cutoff as > %s\n" %
                      (key[0], key[1], eps, minPts, cut))
-    p = device.Pass(ch.dx, ch.dy, int(eps), int(minPts), DBSCAN_VARIANT, int(cut) if cut > 0 else 0, score=False)
-    bbox_h, kind_h = p.bbox.cpu().numpy(), p.kind.cpu().numpy()
-    members, member_kind = p.ys - p.xs, p.member_kind         # Y - X of every clustered PET, its cluster's kind
-    for b in bbox_h[kind_h == 1].tolist():
-        dataI.append([key[0], b[0], b[1], key[1], b[2], b[3]])
-    for b in bbox_h[kind_h == 2].tolist():
-        dataS.append([key[0], b[0], b[1], key[1], b[2], b[3]])
-    inter = members[member_kind == 1] if dataI else empty
-    selfm = members[member_kind == 2] if dataS else empty
-    sys.stderr.write("Clustering %s and %s finished. Estimated %s self-ligation reads and %s inter-ligation reads\n" %
-                     (key[0], key[1], int(selfm.numel()), int(inter.numel())))
-    n_dis, n_dss = int(inter.numel()), int(removed.numel() + selfm.numel())
-    inter = inter.abs()
-    inter = inter[inter > 0]
-    selfd = torch.cat([removed, selfm]).abs()
-    selfd = selfd[selfd > 0]
+    p = device.Pass(ch.dx, ch.dy, int(eps), int(minPts), DBSCAN_VARIANT, int(cut) if cut > 0 else 0, score=False,
+                    stats=(acc.hist, acc.mom))
+    bbox, size, kind = p.records()
     p.close()
-    return key, f, dataI, dataS, n_dis, n_dss, _moments(inter), _moments(selfd), selfd
+    sys.stderr.write("Clustering %s and %s finished. Estimated %s self-ligation reads and %s inter-ligation reads\n" %
+                     (key[0], key[1], int(size[kind == 2].sum()), int(size[kind == 1].sum())))
+    return key, bbox[kind == 1], int((kind == 2).sum())
 
 
-def _round(fs, eps, minPts, cut):
-    """One clustering round over all chromosomes with the cut-off statistics reduced on the GPU.
-    -> (dataI, dataS, n_dis, n_dss, cut_or_None)"""
-    import torch
-    mine = dist.my_share(fs)
-    full = {f: _single_stats(f, eps, minPts, cut) for f in mine}
-    part = {f: r[:8] for f, r in full.items()}           # small host objects travel through the object gather
-    ds = dist.merge_in_order(fs, part)
-    dataI, dataS, n_dis, n_dss, mi, ms = {}, [], 0, 0, [], []
-    used = set()
-    for f, d in zip(fs, ds):
-        if len(d[2]) == 0:                               # pipe.py:121-122: chromosomes without inter-ligation
-            continue                                     # clusters contribute nothing, not even their dss
-        used.add(f)
-        dataI[d[0]] = {"f": d[1], "records": d[2]}
-        dataS.extend(d[3])
-        n_dis += d[4]
-        n_dss += d[5]
-        mi.append(d[6])
-        ms.append(d[7])
-    if len(dataI) == 0 or n_dis == 0 or n_dss == 0:
-        return dataI, dataS, n_dis, n_dss, None
-    local = [full[f][8] for f in mine if f in used]
-    if local:
-        local = torch.cat(local)
-    else:                                                 # this rank owns no contributing chromosome
-        dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
-        local = torch.zeros(0, dtype=torch.int32, device=dev)
-    allself = dist.all_gather_concat(local)
-    srt = torch.sort(allself).values
-    k = int(srt.numel())
-    mid = srt[[(k - 1) // 2, k // 2]].cpu().tolist()
-    cut_2, frags = cut_from_moments(mi, ms, _TwoMiddle(k, mid))
-    return dataI, dataS, n_dis, n_dss, cut_2
+def _round(fs, eps, minPts, cut, weights=None):
+    """One clustering round over the chromosomes this rank owns, the distance cut-off reduced on the GPUs.
+    -> (dataI_2, n_self_clusters, len(dis), len(dss), cut_2 or None, n_chromosomes_with_inter_ligation_clusters);
+    dataI_2 = {key: {"f": f, "records": int32 array [K,4]}} holds THIS rank's chromosomes only; the four numbers after it
+    are global (all ranks)."""
+    acc = _RoundAcc.get()
+    acc.reset()
+    dataI, n_self = {}, 0
+    for f in dist.my_share(fs, _weights(fs) if weights is None else weights):
+        key, inter, ns = _cluster_chrom(f, eps, minPts, cut, acc)
+        if len(inter) == 0:                                # pipe.py:121-122
+            continue
+        dataI[key] = {"f": f, "records": inter}
+        n_self += ns
+    acc.reduce()
+    lo, hi, mom = acc.middle()
+    n_dis, n_dss, n_contrib = int(mom[6]), int(mom[7]), int(mom[8])
+    if n_contrib == 0 or n_dis == 0 or n_dss == 0:
+        return dataI, n_self, n_dis, n_dss, None, n_contrib
+    cut_2 = cut_from_round(mom, lo, hi)
+    if cut_2 is None:
+        # the median left the histogram range, or 2**cut sits on an integer boundary where the summation order of the
+        # moments could flip int(): pool the distances on the host and run the reference's numpy estimate instead
+        _, _, dis, dss = runDBSCAN(fs, eps, minPts, cut, _weights=weights)
+        cut_2 = estIntSelCutFrag(dis, dss)[0]
+    return dataI, n_self, n_dis, n_dss, cut_2, n_contrib
 
 
-class _TwoMiddle:
-    """What cut_from_moments needs of the sorted self-ligation distances: length and the two middle values."""
+def _combine_rounds(rounds):
+    """combineTwice (pipe.py:155-174) over all rounds of one chromosome at once: a record is dropped iff the exact same
+    bbox was produced by an EARLIER round; order = round order, then cluster id.  rounds: list of int [K,4] arrays."""
+    if len(rounds) == 1:
+        return rounds[0]
+    allr = np.concatenate(rounds)
+    rnd = np.repeat(np.arange(len(rounds)), [len(r) for r in rounds])
+    a = allr.astype(np.int64)
+    k1 = (a[:, 0] << 32) | (a[:, 1] & 0xffffffff)
+    k2 = (a[:, 2] << 32) | (a[:, 3] & 0xffffffff)
+    order = np.lexsort((rnd, k2, k1))
+    sk1, sk2, srnd = k1[order], k2[order], rnd[order]
+    head = np.r_[True, (sk1[1:] != sk1[:-1]) | (sk2[1:] != sk2[:-1])]
+    first = srnd[np.flatnonzero(head)][np.cumsum(head) - 1]        # earliest round of each distinct bbox
+    keep = np.empty(len(allr), bool)
+    keep[order] = srnd == first
+    return allr[keep]
 
-    def __init__(self, k, mid):
-        self.k, self.mid = k, mid
 
-    def __len__(self):
-        return self.k
-
-    def __getitem__(self, i):
-        return self.mid[0] if i == (self.k - 1) // 2 else self.mid[1]
+def _rounds(cfs, eps, minPts, cut, max_cut, log, weights=None):
+    """The round loop of cLoops/pipe.py:247-281: clustering rounds with the distance cut-off fed forward, candidates of all
+    rounds merged (combineTwice) and filtered by the final cut-off.  -> (dataI of this rank's chromosomes with records as
+    int64 arrays [K,4] and "first" = first round that produced the chromosome, final cut)"""
+    dataI, cuts, rnd = {}, [cut], 0
+    for ep in eps:
+        for m in minPts:
+            d2, n_self, n_dis, n_dss, cut_2, n_contrib = _round(cfs, ep, m, cut, weights)
+            if n_contrib == 0:
+                log.info("ERROR: no inter-ligation PETs detected for eps %s minPts %s,can't model the distance cutoff,continue anyway" % (ep, m))
+                continue
+            for key, v in d2.items():
+                dataI.setdefault(key, {"f": v["f"], "rounds": [], "first": rnd})["rounds"].append(v["records"])
+            rnd += 1
+            if cut_2 is None:
+                continue
+            log.info("Estimated inter-ligation and self-ligation distance cutoff as %s for eps=%s,minPts=%s" % (cut_2, ep, m))
+            cuts.append(cut_2)
+            cut = cut_2
+    cuts = [c for c in cuts if c > 0]
+    cut = np.max(cuts) if max_cut else np.min(cuts)
+    for key, e in dataI.items():
+        r = _combine_rounds(e.pop("rounds")).astype(np.int64)
+        e["records"] = r[(r[:, 2] + r[:, 3]) // 2 - (r[:, 0] + r[:, 1]) // 2 >= cut]      # filterClusterByDis, pipe.py:130-143
+    return dataI, cut
 
 
 def singleDBSCAN(f, eps, minPts, cut=0):
@@ -195,12 +280,12 @@ def singleDBSCAN(f, eps, minPts, cut=0):
     return key, f, dataI, dataS, dis.tolist(), dss.tolist()
 
 
-def runDBSCAN(fs, eps, minPts, cut=0, cpu=1):
+def runDBSCAN(fs, eps, minPts, cut=0, cpu=1, _weights=None):
     """cLoops/pipe.py:113-127.  Chromosomes owned by this rank are clustered here; results of all ranks
     are merged in file order so every rank returns what the reference's parent process would.  The
     distance collections come back as float64 arrays (the reference returns lists; its only consumer,
     pipe(), wraps them in np.array, pipe.py:259)."""
-    mine = dist.my_share(fs)
+    mine = dist.my_share(fs, _weights)
     part = {f: _single(f, eps, minPts, cut) for f in mine}
     ds = dist.merge_in_order(fs, part)
     dataI, dataS, dis, dss = {}, [], [], []
@@ -241,17 +326,14 @@ def combineTwice(dataI, dataI_2):
     return dataI
 
 
-def runStat(dataI, minPts, cut, cpu, fout, hichip=0):
-    """cLoops/pipe.py:177-203 -> 0 on success, 1 when no loop survives."""
-    _log().info("Starting estimate significance for interactions using distance cutoff as %s" % cut)
-    keys = list(dataI.keys())
-    mine = dist.my_share(keys, weights=[len(dataI[k]["records"]) for k in keys])
-    part = {k: getIntSig(dataI[k]["f"], dataI[k]["records"], minPts, cut) for k in mine}
-    ds = [d for d in dist.merge_in_order(keys, part) if d is not None]
-    if len(ds) == 0:
+def runStat(dataI, minPts, cut, cpu, fout, hichip=0, _local=False):
+    """cLoops/pipe.py:177-203 -> 0 on success, 1 when no loop survives.  ``_local`` (pipe()): ``dataI`` holds only the
+    chromosomes resident on this rank; every rank scores its own and rank 0 concatenates the tables in the reference's
+    order (dict insertion order: first round that produced the chromosome, then file order)."""
+    ds = _score(dataI, minPts, cut, _local)
+    if ds is None:
         _log().error("Something wrong, no loops found, sorry, bye.")
         return 1
-    ds = pd.concat(ds)
     if dist.rank() != 0:
         return 0
     try:
@@ -261,6 +343,68 @@ def runStat(dataI, minPts, cut, cpu, fout, hichip=0):
         _log().warning("Something wrong happend to significance estimation, only output called loops")
         ds.to_csv(fout + "_raw.loop", sep="\t", index_label="loopId")
     return 0
+
+
+def _count(dataI, minPts, cut, _local=False):
+    """GPU half of runStat: per chromosome the counted candidates (cModel.countCandidates) -> {key: counted} of the
+    chromosomes this rank scores."""
+    keys = list(dataI.keys())
+    mine = keys if _local else dist.my_share(keys, weights=[len(dataI[k]["records"]) for k in keys])
+    return {k: cModel.countCandidates(dataI[k]["f"], dataI[k]["records"], minPts, cut) for k in mine}
+
+
+def _tables(dataI, counted, _local=False, done=False):
+    """Host half of runStat: statistics tail per chromosome (``done``: ``counted`` already holds the tables), tables of all
+    ranks concatenated in the reference's order (pipe.py:187-191) -> DataFrame on every rank, or None."""
+    keys = list(dataI.keys())
+    finish = (lambda c: c) if done else cModel.tableFromCounts
+    if _local and dist.world() > 1:
+        part = {k: (dataI[k].get("first", 0), dataI[k].get("order", 0), finish(counted[k])) for k in keys}
+        merged = {}
+        for g in dist.all_gather_objects(part):
+            merged.update(g)
+        ds = [v[2] for _, v in sorted(merged.items(), key=lambda kv: (kv[1][0], kv[1][1])) if v[2] is not None]
+    else:
+        part = {k: finish(c) for k, c in counted.items()}
+        ds = [d for d in dist.merge_in_order(keys, part) if d is not None]
+    if len(ds) == 0:
+        return None
+    return pd.concat(ds)
+
+
+def _score(dataI, minPts, cut, _local=False):
+    """getIntSig over chromosomes (pipe.py:184-191) -> concatenated table on every rank, or None."""
+    _log().info("Starting estimate significance for interactions using distance cutoff as %s" % cut)
+    keys = list(dataI.keys())
+    mine = keys if _local else dist.my_share(keys, weights=[len(dataI[k]["records"]) for k in keys])
+    tables = {k: getIntSig(dataI[k]["f"], dataI[k]["records"], minPts, cut) for k in mine}
+    return _tables(dataI, tables, _local, done=True)
+
+
+def call_loops(cfs, eps, minPts, hic=0, cut=0, max_cut=False, weights=None, tail=True):
+    """pipe() between ingest and output (cLoops/pipe.py:240-284 + 187-196) on chromosomes that are resident in HBM
+    (``_Resident.register`` / ``.jd`` paths): the clustering rounds with cut-off feedback, candidate merging and filtering,
+    range counts, and -- ``tail=True`` -- the statistics tail and the marked loop table.  ``cfs`` lists ALL chromosomes
+    (every rank), ``weights`` their PET counts; each rank works on its own share.
+    -> dict(cut, dataI, counted, table)"""
+    dataI, cut = _rounds(cfs, eps, minPts, cut, max_cut, _log(), weights)
+    for k, f in enumerate(cfs):
+        key = tuple(os.path.split(f)[1].replace("mem:", "").replace(".jd", "").split("-"))
+        if key in dataI:
+            dataI[key]["order"] = k
+    counted = _count(dataI, minPts, 0, _local=True)
+    out = {"cut": int(cut), "dataI": dataI, "counted": counted, "table": None}
+    if tail:
+        out["table"] = finish_loops(out, hic)
+    return out
+
+
+def finish_loops(run, hic=0):
+    """The host tail of call_loops: statistics, de-duplication, tables gathered from all ranks, significance marks."""
+    ds = _tables(run["dataI"], run["counted"], _local=True)
+    if ds is None:
+        return None
+    return markIntSigHic(ds) if hic else markIntSig(ds)
 
 
 def _log():
@@ -295,25 +439,12 @@ def pipe(fs, fout, eps, minPts, chroms="", cpu=1, tmp=0, hic=0, washU=0, juice=0
     cfs, ds = dist.broadcast_object((cfs, ds))
     if eps == 0:
         eps = [estFragSize(ds) * 2]
-    dataI = {}
-    cuts = [cut]
-    for ep in eps:
-        for m in minPts:
-            dataI_2, dataS_2, n_dis, n_dss, cut_2 = _round(cfs, ep, m, cut)
-            if len(dataI_2) == 0:
-                log.info("ERROR: no inter-ligation PETs detected for eps %s minPts %s,can't model the distance cutoff,continue anyway" % (ep, m))
-                continue
-            if cut_2 is None:
-                dataI = combineTwice(dataI, dataI_2)
-                continue
-            log.info("Estimated inter-ligation and self-ligation distance cutoff as %s for eps=%s,minPts=%s" % (cut_2, ep, m))
-            cuts.append(cut_2)
-            cut = cut_2
-            dataI = combineTwice(dataI, dataI_2)
-    cuts = [c for c in cuts if c > 0]
-    cut = np.max(cuts) if max_cut else np.min(cuts)
-    dataI = filterClusterByDis(dataI, cut)
-    e = runStat(dataI, minPts, 0, cpu, fout, hic)
+    dataI, cut = _rounds(cfs, eps, minPts, cut, max_cut, log)
+    for k, f in enumerate(cfs):                               # file order, for the final concatenation
+        key = tuple(os.path.split(f)[1].replace(".jd", "").split("-"))
+        if key in dataI:
+            dataI[key]["order"] = k
+    e = runStat(dataI, minPts, 0, cpu, fout, hic, _local=True)
     _Resident.clear()
     dist.barrier()
     if dist.rank() != 0:

@@ -121,6 +121,9 @@ CLOOPS_API void cloops_coverage_release(cloops_coverage* cov, void* stream);  /*
  * d_out int32[m,123] = ra, rb, rab, na[10], nb[10], C[10][10] row-major (i over A windows). */
 CLOOPS_API int cloops_range_counts(const cloops_coverage* cov, const int32_t* d_cand, int64_t m, int32_t* d_out, void* stream);
 /* only ra, rb, rab (getPETsforRegions, cModel.py:72-80): d_out int32[m,3] */
+/* measurement aid: algorithmic work of the range-count kernel for a candidate list: h_work[0] / h_work[1] = PETs
+ * with X / with Y inside the hull of each candidate's windows, summed; win = 5 (cloops_range_counts) or 0 (cloops_region_pets) */
+CLOOPS_API int cloops_range_work(const cloops_coverage* cov, const int32_t* d_cand, int64_t m, int32_t win, uint64_t* h_work, void* stream);
 CLOOPS_API int cloops_region_pets(const cloops_coverage* cov, const int32_t* d_cand, int64_t m, int32_t* d_out, void* stream);
 
 /* ---- one pass of the whole hot path over one chromosome, as ONE call ----------------------------------
@@ -159,6 +162,8 @@ CLOOPS_API const void* cloops_pass_device_ptr(const cloops_pass* p, int which);
 /* copy results into HOST buffers (each may be NULL) and synchronise the stream once */
 CLOOPS_API int cloops_pass_fetch(const cloops_pass* p, int32_t* h_bbox, uint8_t* h_kind, uint8_t* h_member_kind, int32_t* h_counts,
                       void* stream);
+/* candidate records for the host (pipe.py:76-102): h_bbox int32[k,4], h_size int32[k], h_kind u8[k]; any may be NULL; one sync */
+CLOOPS_API int cloops_pass_fetch_records(const cloops_pass* p, int32_t* h_bbox, int32_t* h_size, uint8_t* h_kind, void* stream);
 CLOOPS_API void cloops_pass_free(cloops_pass* p, void* stream);
 
 #ifdef __cplusplus

@@ -52,42 +52,67 @@ if dist.rank() == 0:
     open(os.path.join(out, "ok"), "w").write("ok")
 assert dist.broadcast_object({"cut": 4601} if dist.rank() == 0 else None) == {"cut": 4601}
 
-# device-side cut-off reduction across ranks (CPU tensors over gloo here, CUDA tensors over NCCL on the box)
+# device-side cut-off reduction across ranks: per-chromosome contributions to the round accumulators, summed with ONE
+# all-reduce (CPU tensors over gloo here, CUDA tensors over NCCL on the box), then the reference's estimate (ests.py:36-61)
 import torch  # noqa: E402
 
-from cloops_b200 import ests  # noqa: E402
+from cloops_b200 import _lib, ests  # noqa: E402
 
 rng = np.random.default_rng(5)
 dist_i = {f: rng.integers(5000, 400000, 300 + 40 * k) for k, f in enumerate(files)}
 dist_s = {f: rng.integers(40, 3000, 500 + 70 * k) for k, f in enumerate(files)}
 
 
-def mom(v):
-    x = np.log2(v.astype(np.float64))
-    return (len(x), float(x.mean()), float(((x - x.mean()) ** 2).sum()))
+class CpuAcc(pipe._RoundAcc):
+    """The accumulators as CPU tensors; middle() restated with numpy (the CUDA one is cloops_round_middle)."""
+
+    def __init__(self):
+        self.hist = torch.zeros(_lib.ROUND_HIST_BINS + 1, dtype=torch.int32)
+        self.mom = torch.zeros(_lib.ROUND_MOM, dtype=torch.float64)
+
+    def middle(self):
+        cum = np.cumsum(self.hist.numpy().astype(np.int64))
+        k = int(self.mom[3])
+        return int(np.searchsorted(cum, (k - 1) // 2, side="right")), int(np.searchsorted(cum, k // 2, side="right")), self.mom.tolist()
 
 
-def fake_stats(f, eps, minPts, cut=0):
+acc = CpuAcc()
+pipe._RoundAcc.get = classmethod(lambda cls: acc)
+clustered = []
+
+
+def fake_cluster(f, eps, minPts, cut, acc):
+    clustered.append(f)
     c = f.split("-")[0]
-    recs = [[c, 1, 2, c, 30, 40]] if c != "chrE" else []
-    return (c, c), f, recs, [], len(dist_i[f]), len(dist_s[f]), mom(dist_i[f]), mom(dist_s[f]), torch.from_numpy(dist_s[f].astype(np.int32))
+    if c == "chrE":                                       # no inter-ligation clusters: contributes nothing (pipe.py:121-122)
+        return (c, c), np.zeros((0, 4), np.int32), 3
+    li, ls = np.log2(dist_i[f].astype(np.float64)), np.log2(dist_s[f].astype(np.float64))
+    acc.mom += torch.tensor([len(li), li.sum(), (li * li).sum(), len(ls), ls.sum(), (ls * ls).sum(), len(li), len(ls), 1] + [0] * 7, dtype=torch.float64)
+    acc.hist += torch.from_numpy(np.bincount(dist_s[f], minlength=_lib.ROUND_HIST_BINS + 1).astype(np.int32))
+    return (c, c), np.array([[1, 2, 9000030 + eps, 9000040 + eps]], np.int32), 1
 
 
-pipe._single_stats = fake_stats
-dataI, dataS, n_dis, n_dss, cut = pipe._round(files, 1000, 5, 0)
-used = files[:4]                                         # chrE has no inter-ligation records: excluded (pipe.py:121-122)
+pipe._cluster_chrom = fake_cluster
+w = [weights[f] for f in files]
+dataI, n_self, n_dis, n_dss, cut, n_contrib = pipe._round(files, 1000, 5, 0, w)
+used = files[:4]
 want = ests.estIntSelCutFrag(np.concatenate([dist_i[f] for f in used]), np.concatenate([dist_s[f] for f in used]))[0]
 assert cut == want, (cut, want)
-assert n_dis == sum(len(dist_i[f]) for f in used) and n_dss == sum(len(dist_s[f]) for f in used)
+assert n_contrib == 4 and n_dis == sum(len(dist_i[f]) for f in used) and n_dss == sum(len(dist_s[f]) for f in used)
+assert sorted(k[0] + "-" + k[0] + ".jd" for k in dataI) == sorted(set(clustered) & set(used))      # local chromosomes only
 got = dist.all_gather_concat(torch.arange(3 + dist.rank(), dtype=torch.int32))
 assert got.tolist() == [0, 1, 2, 0, 1, 2, 3]
+assert ests.cut_from_round([10, 100.0, 1001.0, 10, 50.0, 251.0] + [0] * 10, 1 << 20, 5) is None          # median outside the histogram
+assert pipe._combine_rounds([np.array([[1, 2, 3, 4], [5, 6, 7, 8]]), np.array([[5, 6, 7, 8], [9, 9, 9, 9], [9, 9, 9, 9]]),
+                             np.array([[1, 2, 3, 4], [0, 0, 0, 0]])]).tolist() == [[1, 2, 3, 4], [5, 6, 7, 8], [9, 9, 9, 9], [9, 9, 9, 9], [0, 0, 0, 0]]
 
 # pipe() itself under two ranks (ADVICE r1): rank 0 alone decides about the output directory and every rank follows.
 # (1) existing directory -> every rank returns, no collective is left hanging; (2) fresh directory -> the run completes.
 pipe.parseRawBedpe2 = lambda fs, fout, chroms, cut, log: list(files)
+pipe._weights = lambda fs: [weights[f] for f in fs]
 calls = []
 orig_round = pipe._round
-pipe._round = lambda fs, ep, m, cut: (calls.append((ep, m, cut)), orig_round(fs, ep, m, cut))[1]
+pipe._round = lambda fs, ep, m, cut, weights=None: (calls.append((ep, m, cut)), orig_round(fs, ep, m, cut, weights))[1]
 exists = os.path.join(out, "exists")
 if dist.rank() == 0:
     os.mkdir(exists)
@@ -95,9 +120,16 @@ dist.barrier()
 assert pipe.pipe(["x.bedpe"], exists, [1000], [5]) is None and calls == []
 dist.barrier()
 fresh = os.path.join(out, "fresh")
+seen_records = {}
+pipe.getIntSig = lambda f, records, minPts, cut: (seen_records.__setitem__(f, np.asarray(records).tolist()), pd.DataFrame(
+    {"ES": [3.0], "FDR": [0.0], "hypergeometric_p-value": [1e-20], "poisson_p-value": [1e-9], "binomial_p-value": [1e-9]}, index=["%s-0" % f]))[1]
 pipe.pipe(["x.bedpe"], fresh, [1000, 2000], [5], tmp=1)
 assert [c[:2] for c in calls] == [(1000, 5), (2000, 5)] and calls[1][2] == want, calls
+for f, recs in seen_records.items():                                # both rounds' records of the rank's own chromosomes, merged
+    assert recs == [[1, 2, 9001030, 9001040], [1, 2, 9002030, 9002040]], recs
 dist.barrier()
 if dist.rank() == 0:
     assert os.path.isdir(fresh) and os.path.isfile(fresh + ".loop")
+    tab = pd.read_csv(fresh + ".loop", sep="\t", index_col=0)
+    assert list(tab.index) == ["%s-0" % f for f in files[:4]], list(tab.index)      # file order, from all ranks
     open(os.path.join(out, "ok_pipe"), "w").write("ok")

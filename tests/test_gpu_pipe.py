@@ -33,8 +33,8 @@ def test_pipe_m1_chr21(need_gpu, gold_dir, tmp_path, monkeypatch):
     cuts = []
     orig = pipe._round
 
-    def spy(fs, eps, minPts, cut):
-        r = orig(fs, eps, minPts, cut)
+    def spy(fs, eps, minPts, cut, weights=None):
+        r = orig(fs, eps, minPts, cut, weights)
         cuts.append((r[2], r[3], r[4]))
         return r
 
@@ -66,7 +66,7 @@ def test_run_dbscan_round_records(need_gpu, gold_dir, tmp_path):
         assert (len(dis), len(dss)) == (int(gold["round_ndis"][k]), int(gold["round_ndss"][k]))
         # host estimate (the reference's numpy path) and the device-side reduction give the same integer cut
         host_cut = pipe.estIntSelCutFrag(np.array(dis), np.array(dss))[0]
-        _, _, n_dis, n_dss, dev_cut = pipe._round([f], eps, 5, cut)
+        _, _, n_dis, n_dss, dev_cut, _ = pipe._round([f], eps, 5, cut)
         assert (n_dis, n_dss, dev_cut) == (len(dis), len(dss), host_cut) and host_cut == int(gold["round_cut_out"][k])
 
 
@@ -104,7 +104,7 @@ def test_pipe_multi_chrom_hic(need_gpu, gold_dir, tmp_path, monkeypatch):
     monkeypatch.chdir(tmp_path)
     cuts = []
     orig = pipe._round
-    monkeypatch.setattr(pipe, "_round", lambda fs, e, m, c: (lambda r: (cuts.append((r[2], r[3], r[4])), r)[1])(orig(fs, e, m, c)))
+    monkeypatch.setattr(pipe, "_round", lambda fs, e, m, c, w=None: (lambda r: (cuts.append((r[2], r[3], r[4])), r)[1])(orig(fs, e, m, c, w)))
     pipe.pipe([bedpe], "out", [1000, 2000], [8, 5], cpu=1, tmp=0, hic=1)
     assert np.array_equal(np.array(cuts, np.int64), gold["cuts"])
     assert open(tmp_path / "out.loop", "rb").read() == open(os.path.join(gold_dir, "multi_hic.loop"), "rb").read()
