@@ -123,6 +123,23 @@ def _stats(c: np.ndarray, N: int):
     return ra, rb, rab, es, fdr, hyp, pop, nbp
 
 
+_POOL = None
+
+
+def _chunked(fn, *cols, chunk=2048):
+    """fn(*cols) evaluated chunk by chunk on a few host threads: scipy's distribution ufuncs release the GIL and cost tens of
+    microseconds per candidate at Hi-C depth (hypergeom.sf with N ~ 10^7); every element is computed exactly as in one call."""
+    global _POOL
+    n = len(cols[0])
+    if n <= chunk:
+        return fn(*cols)
+    if _POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _POOL = ThreadPoolExecutor(max_workers=max(1, min(32, os.cpu_count() or 1)))
+    parts = _POOL.map(lambda a: fn(*(c[a:a + chunk] for c in cols)), range(0, n, chunk))
+    return np.concatenate(list(parts))
+
+
 def _stats_batch(counts: np.ndarray, N: int):
     """_stats for K candidates at once -> eight arrays.  Same operations per candidate (the joint counts
     are integers, so their sums are exact in any order; the density mean keeps numpy's row-wise pairwise
@@ -142,11 +159,28 @@ def _stats_batch(counts: np.ndarray, N: int):
         mrabs = np.mean(rabs, axis=1)
         npos = (rabs > 0).sum(axis=1)
         es = np.where(mrabs > 0, rab / (rabs.sum(axis=1) / np.maximum(npos, 1)), np.inf)
-        hyp = np.maximum(1e-300, hypergeom.sf(rab - 1.0, N, ra, rb))
-        pop = np.maximum(1e-300, poisson.sf(rab - 1.0, mrabs))
+        hyp = np.maximum(1e-300, _chunked(lambda k, a, b: hypergeom.sf(k, N, a, b), rab - 1.0, ra, rb))
+        pop = np.maximum(1e-300, _chunked(poisson.sf, rab - 1.0, mrabs))
         bp = np.mean(nbps, axis=1) * ra * rb / N
-        nbp = np.maximum(1e-300, binom.sf(rab - 1.0, N - rab, bp))
+        nbp = np.maximum(1e-300, _chunked(binom.sf, rab - 1.0, N - rab, bp))
     return ra, rb, rab, es, fdr, hyp, pop, nbp
+
+
+def _stats_binom(counts: np.ndarray, N: int):
+    """The part of _stats_batch removeDup needs (cModel.py:235-258 looks at the binomial p and rab / ra / rb only):
+    -> ra, rb, rab, nbp.  Element for element the same operations as _stats_batch."""
+    c = np.asarray(counts)
+    K = c.shape[0]
+    ra, rb, rab = (c[:, k].astype(np.int64) for k in range(3))
+    na = c[:, 3:13].astype(np.float64)
+    nb = c[:, 13:23].astype(np.int64)
+    joint = c[:, 23:123].astype(np.float64).reshape(K, 10, 10)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        dens = joint / (na[:, :, None] * nb[:, None, :])
+        nbps = np.where(joint > 0, dens, 0.0).reshape(K, 100)
+        bp = np.mean(nbps, axis=1) * ra * rb / N
+        nbp = np.maximum(1e-300, _chunked(binom.sf, rab - 1.0, N - rab, bp))
+    return ra, rb, rab, nbp
 
 
 def getMultiplePsFdr(iva, ivb, model, N, win=5):
@@ -187,78 +221,52 @@ def _end_overlap(xa, xb, ya, yb):
     return (((ya <= xa) & (xa <= yb)) | ((ya <= xb) & (xb <= yb)) | ((xa <= ya) & (ya <= xb)) | ((xa <= yb) & (yb <= xb)))
 
 
+def _remove_dup_index(a0, a1, b0, b1, bp, dens, bpcut=1e-5):
+    """removeDup on columns (one chromosome): -> indices of the surviving loops in the reference's output order.  The greedy
+    grouping and the choice of winners run in host C++ (``cloops_remove_dup``, csrc/removedup.cu); groups whose maximum
+    density is shared come back as tie lists and are resolved here with the reference's expression (pandas'
+    ``Series.sort_values(ascending=False)`` spelled out: reverse, argsort ascending with numpy's quicksort, reverse)."""
+    import ctypes as C
+    from . import _lib
+    n = len(a0)
+    cols = [np.ascontiguousarray(v, dtype=np.int64) for v in (a0, a1, b0, b1)]
+    bp = np.ascontiguousarray(bp, dtype=np.float64)
+    dens = np.ascontiguousarray(dens, dtype=np.float64)
+    keep, tie_start, tie_members = np.empty(max(n, 1), np.int64), np.empty(n + 1, np.int64), np.empty(max(n, 1), np.int64)
+    n_keep, n_ties = C.c_int64(0), C.c_int64(0)
+    _lib.check(_lib.lib().cloops_remove_dup(*(c.ctypes.data for c in cols), bp.ctypes.data, dens.ctypes.data, n, float(bpcut),
+                                            keep.ctypes.data, C.addressof(n_keep), tie_start.ctypes.data, tie_members.ctypes.data,
+                                            C.addressof(n_ties)))
+    keep = keep[:n_keep.value]
+    for g in range(n_ties.value):
+        members = tie_members[tie_start[g]:tie_start[g + 1]]
+        vals = dens[members]
+        order = np.arange(len(vals))[::-1][vals[::-1].argsort(kind="quicksort")][::-1]
+        keep[keep == -(g + 1)] = members[int(order[0])]
+    return keep
+
+
 def removeDup(ds, bpcut=1e-5):
-    """cModel.py:198-259: greedy grouping of overlapping loops in key order (first member leads its
-    group), then per group keep the densest member among those with binomial p <= bpcut.  Same
-    grouping and the same winner as the reference; the inner loop runs vectorised over the pending
-    loops instead of pair by pair."""
+    """cModel.py:198-259: greedy grouping of overlapping loops in key order (first member leads its group), then per group
+    keep the densest member among those with binomial p <= bpcut.  Same grouping, same winners and same output order as
+    the reference; the pair loop runs as a sweep in host C++."""
     keys = list(ds.keys())
-    n = len(keys)
-    if n == 0:
+    if len(keys) == 0:
         return {}
     ivs = [(parseIv(ds[k]["iva"]), parseIv(ds[k]["ivb"])) for k in keys]
-    chrom_ids = {}
-    chrom = np.array([chrom_ids.setdefault((a[0], b[0]), len(chrom_ids)) for a, b in ivs])
-    a0 = np.array([a[1] for a, _ in ivs], dtype=np.int64)
-    a1 = np.array([a[2] for a, _ in ivs], dtype=np.int64)
+    chroms = set((a[0], b[0]) for a, b in ivs)
+    if len(chroms) > 1:                                  # loops of several chromosome pairs: they never overlap (:188-189)
+        ids = {c: i for i, c in enumerate(sorted(chroms))}
+        off = np.array([ids[(a[0], b[0])] for a, b in ivs], dtype=np.int64) << 40
+    else:
+        off = np.zeros(len(keys), np.int64)
+    a0 = np.array([a[1] for a, _ in ivs], dtype=np.int64) + off
+    a1 = np.array([a[2] for a, _ in ivs], dtype=np.int64) + off
     b0 = np.array([b[1] for _, b in ivs], dtype=np.int64)
     b1 = np.array([b[2] for _, b in ivs], dtype=np.int64)
-    taken = np.zeros(n, dtype=bool)
-    uniqueds = {}
-    groups = {}
-    # Two loops can only overlap if their left anchors intersect, i.e. a0_j lies in [a0_i - wmax, a1_i]
-    # (wmax = widest left anchor).  Looking candidates up in an a0-sorted index keeps the reference's
-    # greedy, order-dependent grouping (leader = first key, members in key order) at O(n log n).
-    proper = bool(np.all(a0 <= a1) and np.all(b0 <= b1))
-    if proper:
-        order = np.argsort(a0, kind="stable")
-        a0s = a0[order]
-        wmax = int((a1 - a0).max())
-    if proper:
-        # loops whose left anchor cannot intersect any other left anchor are unique without any test
-        los = np.searchsorted(a0s, a0 - wmax, side="left")
-        his = np.searchsorted(a0s, a1, side="right")
-        lonely = (his - los) <= 1
-    for i in range(n - 1):
-        if taken[i]:
-            continue
-        if proper:
-            if lonely[i]:
-                uniqueds[keys[i]] = ds[keys[i]]
-                continue
-            lo, hi = los[i], his[i]
-            j = order[lo:hi]
-            j = np.sort(j[(j > i)])
-            j = j[~taken[j]]
-        else:
-            j = np.arange(i + 1, n)
-            j = j[~taken[i + 1:]]
-        if len(j):
-            hit = (chrom[j] == chrom[i]) & _end_overlap(a0[i], a1[i], a0[j], a1[j]) & _end_overlap(b0[i], b1[i], b0[j], b1[j])
-            j = j[hit]
-        if len(j):
-            groups[i] = [i] + j.tolist()
-            taken[i] = True
-            taken[j] = True
-        else:
-            uniqueds[keys[i]] = ds[keys[i]]
-    for lead, members in groups.items():
-        ts = {}
-        for t in members:
-            d = ds[keys[t]]
-            if d["binomial_p-value"] > bpcut:
-                continue
-            ts[keys[t]] = float(d["rab"]) / d["ra"] / d["rb"]
-        if not ts:
-            continue
-        # pandas' ``Series.sort_values(ascending=False)`` (the reference's choice of winner, :255-258),
-        # spelled out: reverse, argsort ascending with numpy's quicksort, reverse again
-        tkeys = list(ts.keys())
-        vals = np.array([ts[t] for t in tkeys], dtype=np.float64)
-        order = np.arange(len(vals))[::-1][vals[::-1].argsort(kind="quicksort")][::-1]
-        win = tkeys[int(order[0])]
-        uniqueds[win] = ds[win]
-    return uniqueds
+    bp = np.array([ds[k]["binomial_p-value"] for k in keys], dtype=np.float64)
+    dens = np.array([float(ds[k]["rab"]) / ds[k]["ra"] / ds[k]["rb"] for k in keys], dtype=np.float64)
+    return {keys[i]: ds[keys[i]] for i in _remove_dup_index(a0, a1, b0, b1, bp, dens, bpcut).tolist()}
 
 
 def countCandidates(f, records, minPts, discut):
@@ -294,31 +302,38 @@ def countCandidates(f, records, minPts, discut):
     return {"N": N, "names": names, "cand": cand, "keep": keep, "dist": dist_all, "counts": counts}
 
 
+COLUMNS = ["distance", "ra", "rb", "rab", "ES", "FDR", "hypergeometric_p-value", "poisson_p-value", "binomial_p-value", "iva", "ivb"]
+
+
 def tableFromCounts(c):
     """The host half of getIntSig (cModel.py:295-331): the reference's numpy / scipy statistics on the counted integers,
-    key numbering (:280,292), removeDup twice (:318,322), Bonferroni (:327-330).  -> DataFrame or None."""
+    key numbering (:280,292), removeDup twice (:318,322), Bonferroni (:327-330).  -> DataFrame or None.  Works on columns;
+    the frame it returns equals the reference's ``pd.DataFrame(ds).T`` (object columns, dict insertion order)."""
     if c is None:
         return None
     N, (chrom_a, chrom_b), cand, keep, dist_all, counts = c["N"], c["names"], c["cand"], c["keep"], c["dist"], c["counts"]
-    ds = {}
-    if len(keep):
-        ra, rb, rab, es, fdr, hyp, pop, nbp = _stats_batch(counts, N)
-        chrom = chrom_a
-        for i, k in enumerate(keep.tolist()):                  # key number = accepted so far (cModel.py:280,292)
-            ds["%s-%s-%s" % (chrom_a, chrom_b, i)] = {
-                "distance": float(dist_all[k]), "ra": int(ra[i]), "rb": int(rb[i]), "rab": int(rab[i]), "ES": es[i], "FDR": fdr[i],
-                "hypergeometric_p-value": hyp[i], "poisson_p-value": pop[i], "binomial_p-value": nbp[i],
-                "iva": "%s:%s-%s" % (chrom, int(cand[k, 0]), int(cand[k, 1])), "ivb": "%s:%s-%s" % (chrom, int(cand[k, 2]), int(cand[k, 3])),
-            }
-    if len(ds) == 0:
+    if len(keep) == 0:
         return None
-    ds = removeDup(ds)
-    if len(ds) == 0:
-        return None
-    ds = removeDup(ds)
-    if len(ds) == 0:
-        return None
-    ds = pd.DataFrame(ds).T
+    # removeDup looks at the binomial p and the density only: those are evaluated for every scored candidate, the other
+    # statistics (hypergeom.sf costs ~60 us per candidate at N ~ 10^7) for the survivors -- element for element the same calls
+    ra, rb, rab, nbp = _stats_binom(counts, N)
+    a0, a1, b0, b1 = (cand[keep, k] for k in range(4))
+    dens = rab.astype(np.float64) / ra / rb                     # float(rab) / ra / rb (:244)
+    idx = np.arange(len(keep))                                  # key number = accepted so far (cModel.py:280,292)
+    for _ in range(2):
+        idx = idx[_remove_dup_index(a0[idx], a1[idx], b0[idx], b1[idx], nbp[idx], dens[idx])]
+        if len(idx) == 0:
+            return None
+    full = _stats_batch(counts[idx], N)
+    assert np.array_equal(full[7], nbp[idx])
+    es, fdr, hyp, pop = (np.empty(len(keep), np.float64) for _ in range(4))
+    es[idx], fdr[idx], hyp[idx], pop[idx] = full[3], full[4], full[5], full[6]
+    obj = lambda v: np.asarray(v)[idx].astype(object)           # python ints / floats, as the reference's dict values
+    iva = np.array(["%s:%s-%s" % (chrom_a, x, y) for x, y in zip(a0[idx].tolist(), a1[idx].tolist())], dtype=object)
+    ivb = np.array(["%s:%s-%s" % (chrom_a, x, y) for x, y in zip(b0[idx].tolist(), b1[idx].tolist())], dtype=object)
+    cols = {"distance": obj(dist_all[keep]), "ra": obj(ra), "rb": obj(rb), "rab": obj(rab), "ES": obj(es), "FDR": obj(fdr),
+            "hypergeometric_p-value": obj(hyp), "poisson_p-value": obj(pop), "binomial_p-value": obj(nbp), "iva": iva, "ivb": ivb}
+    ds = pd.DataFrame(cols, index=["%s-%s-%s" % (chrom_a, chrom_b, i) for i in idx.tolist()], columns=COLUMNS)
     ds["poisson_p-value_corrected"] = getBonPvalues(ds["poisson_p-value"])
     ds["binomial_p-value_corrected"] = getBonPvalues(ds["binomial_p-value"])
     ds["hypergeometric_p-value_corrected"] = getBonPvalues(ds["hypergeometric_p-value"])

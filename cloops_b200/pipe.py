@@ -381,7 +381,7 @@ def _score(dataI, minPts, cut, _local=False):
     return _tables(dataI, tables, _local, done=True)
 
 
-def call_loops(cfs, eps, minPts, hic=0, cut=0, max_cut=False, weights=None, tail=True):
+def call_loops(cfs, eps, minPts, hic=0, cut=0, max_cut=False, weights=None, tail=True, mark=True):
     """pipe() between ingest and output (cLoops/pipe.py:240-284 + 187-196) on chromosomes that are resident in HBM
     (``_Resident.register`` / ``.jd`` paths): the clustering rounds with cut-off feedback, candidate merging and filtering,
     range counts, and -- ``tail=True`` -- the statistics tail and the marked loop table.  ``cfs`` lists ALL chromosomes
@@ -392,10 +392,18 @@ def call_loops(cfs, eps, minPts, hic=0, cut=0, max_cut=False, weights=None, tail
         key = tuple(os.path.split(f)[1].replace("mem:", "").replace(".jd", "").split("-"))
         if key in dataI:
             dataI[key]["order"] = k
-    counted = _count(dataI, minPts, 0, _local=True)
-    out = {"cut": int(cut), "dataI": dataI, "counted": counted, "table": None}
-    if tail:
-        out["table"] = finish_loops(out, hic)
+    out = {"cut": int(cut), "dataI": dataI, "counted": None, "table": None}
+    if not tail:
+        out["counted"] = _count(dataI, minPts, 0, _local=True)
+        return out
+    # the statistics tail of one chromosome (host threads) runs while the GPU counts the next one
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=1) as ex:
+        futs = {k: ex.submit(cModel.tableFromCounts, cModel.countCandidates(dataI[k]["f"], dataI[k]["records"], minPts, 0)) for k in dataI}
+        tables = {k: f.result() for k, f in futs.items()}
+    ds = _tables(dataI, tables, _local=True, done=True)
+    if ds is not None:
+        out["table"] = (markIntSigHic(ds) if hic else markIntSig(ds)) if mark else ds
     return out
 
 
@@ -439,12 +447,19 @@ def pipe(fs, fout, eps, minPts, chroms="", cpu=1, tmp=0, hic=0, washU=0, juice=0
     cfs, ds = dist.broadcast_object((cfs, ds))
     if eps == 0:
         eps = [estFragSize(ds) * 2]
-    dataI, cut = _rounds(cfs, eps, minPts, cut, max_cut, log)
-    for k, f in enumerate(cfs):                               # file order, for the final concatenation
-        key = tuple(os.path.split(f)[1].replace(".jd", "").split("-"))
-        if key in dataI:
-            dataI[key]["order"] = k
-    e = runStat(dataI, minPts, 0, cpu, fout, hic, _local=True)
+    log.info("Starting estimate significance for interactions using distance cutoff as 0")
+    ds = call_loops(cfs, eps, minPts, hic, cut, max_cut, mark=False)["table"]       # pipe.py:247-284 (+ 184-191)
+    e = 0
+    if ds is None:
+        log.error("Something wrong, no loops found, sorry, bye.")
+        e = 1
+    elif dist.rank() == 0:                                    # pipe.py:191-202
+        try:
+            ds = markIntSigHic(ds) if hic else markIntSig(ds)
+            ds.to_csv(fout + ".loop", sep="\t", index_label="loopId")
+        except Exception:
+            log.warning("Something wrong happend to significance estimation, only output called loops")
+            ds.to_csv(fout + "_raw.loop", sep="\t", index_label="loopId")
     _Resident.clear()
     dist.barrier()
     if dist.rank() != 0:

@@ -166,6 +166,16 @@ CLOOPS_API int cloops_pass_fetch(const cloops_pass* p, int32_t* h_bbox, uint8_t*
 CLOOPS_API int cloops_pass_fetch_records(const cloops_pass* p, int32_t* h_bbox, int32_t* h_size, uint8_t* h_kind, void* stream);
 CLOOPS_API void cloops_pass_free(cloops_pass* p, void* stream);
 
+/* ---- removeDup (cLoops/cModel.py:198-259) for the loops of one chromosome: host C++ --------------------------------
+ * a0,a1,b0,b1 int64[n]: the two anchors of each loop in key order; bp double[n]: binomial p; dens double[n]: rab/ra/rb.
+ * keep int64[n] receives the surviving loops in the reference's output order (unique loops in key order, then one winner
+ * per overlap group in leader order); an entry -(g+1) stands for tie group g, whose eligible members are
+ * tie_members[tie_start[g] .. tie_start[g+1]) (several share the maximum): the reference's winner then depends on the sort
+ * pandas uses, and the caller resolves it with the reference's own expression.  tie_start int64[n+1], tie_members int64[n]. */
+CLOOPS_API int cloops_remove_dup(const int64_t* a0, const int64_t* a1, const int64_t* b0, const int64_t* b1, const double* bp,
+                      const double* dens, int64_t n, double bpcut, int64_t* keep, int64_t* n_keep, int64_t* tie_start,
+                      int64_t* tie_members, int64_t* n_ties);
+
 #ifdef __cplusplus
 }
 #endif

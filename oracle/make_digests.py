@@ -43,6 +43,7 @@ def case_digest(X, Y, variant, eps, minPts, cut, score=False):
     lab = np.full(len(X), -1, np.int32)
     lab[m], info = coracle.dbscan(X64[m], Y64[m], eps, minPts, variant, return_info=True)
     bbox, size, kind = coracle.cluster_records(X64, Y64, lab)
+    bbox[size == 0] = 0                      # ids without members (v1 keeps the gaps of deleted clusters, cDBSCAN.py:149-152)
     d = {"labels": sha(lab), "n_labelled": int((lab >= 0).sum()), "n_clusters": int(info["clusters"]), "n_dead": int(info["dead"]),
          "bbox": sha(bbox.astype(np.int32)), "kind": sha(kind), "n_inter": int((kind == 1).sum())}
     if score:

@@ -121,8 +121,9 @@ assert pipe.pipe(["x.bedpe"], exists, [1000], [5]) is None and calls == []
 dist.barrier()
 fresh = os.path.join(out, "fresh")
 seen_records = {}
-pipe.getIntSig = lambda f, records, minPts, cut: (seen_records.__setitem__(f, np.asarray(records).tolist()), pd.DataFrame(
-    {"ES": [3.0], "FDR": [0.0], "hypergeometric_p-value": [1e-20], "poisson_p-value": [1e-9], "binomial_p-value": [1e-9]}, index=["%s-0" % f]))[1]
+pipe.cModel.countCandidates = lambda f, records, minPts, cut: (f, np.asarray(records).tolist())
+pipe.cModel.tableFromCounts = lambda c: (seen_records.__setitem__(c[0], c[1]), pd.DataFrame(
+    {"ES": [3.0], "FDR": [0.0], "hypergeometric_p-value": [1e-20], "poisson_p-value": [1e-9], "binomial_p-value": [1e-9]}, index=["%s-0" % c[0]]))[1]
 pipe.pipe(["x.bedpe"], fresh, [1000, 2000], [5], tmp=1)
 assert [c[:2] for c in calls] == [(1000, 5), (2000, 5)] and calls[1][2] == want, calls
 for f, recs in seen_records.items():                                # both rounds' records of the rank's own chromosomes, merged

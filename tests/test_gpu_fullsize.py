@@ -58,10 +58,12 @@ def test_fullsize_labels_records_counts(digests, name, run, score):
     if variant != 3:
         assert info["n_dead"] == want["n_dead"] or variant == 1
     bbox, size, kind, row_kind = device.cluster_summary_device(dx, dy, lab_t, info["n_clusters"])
-    assert sha(bbox.cpu().numpy()) == want["bbox"] and sha(kind.cpu().numpy()) == want["kind"]
+    bbox_h = bbox.cpu().numpy()
+    bbox_h[size.cpu().numpy() == 0] = 0          # ids without members (v1 keeps the gaps of deleted clusters)
+    assert sha(bbox_h) == want["bbox"] and sha(kind.cpu().numpy()) == want["kind"]
     if score:
         kind_h = kind.cpu().numpy()
-        cand = bbox.cpu().numpy()[kind_h == 1].astype(np.int64)
+        cand = bbox_h[kind_h == 1].astype(np.int64)
         cand[:, 0] = np.maximum(cand[:, 0], 0)
         cand[:, 2] = np.maximum(cand[:, 2], 0)
         cov = device.Coverage(dx, dy)

@@ -91,6 +91,39 @@ def test_removedup_and_marks_vs_live_reference():
             assert cModel.markIntSigHic(a.copy())["significant"].tolist() == ns.cModel.markIntSigHic(b.copy())["significant"].tolist()
 
 
+def test_table_from_counts_equals_reference_tail(gold):
+    """The columnar statistics tail (tableFromCounts) against the reference's own tail (cModel.py:295-331: dict of dicts,
+    removeDup twice, DataFrame(ds).T, Bonferroni) on the same counted integers: identical CSV text."""
+    ns = ref_shim.load()
+    rng = np.random.default_rng(3)
+    N = int(gold["sig_N"])
+    for trial in range(6):
+        K = int(rng.integers(1, 400))
+        counts = gold["sig_ints200"][rng.integers(0, 200, K)].astype(np.int32)
+        a0 = rng.integers(0, 40000, K); a1 = a0 + rng.integers(0, 1500, K)
+        b0 = a0 + rng.integers(3000, 30000, K); b1 = b0 + rng.integers(0, 1500, K)
+        cand = np.stack([a0, a1, b0, b1], axis=1).astype(np.int64)
+        keep = np.sort(rng.choice(K, max(1, K // 2), replace=False))
+        dist = np.abs((cand[:, 2] + cand[:, 3]) / 2.0 - (cand[:, 0] + cand[:, 1]) / 2.0)
+        got = cModel.tableFromCounts({"N": N, "names": ("chr7", "chr7"), "cand": cand, "keep": keep, "dist": dist, "counts": counts[keep]})
+        ds = {}
+        for i, k in enumerate(keep.tolist()):
+            ra, rb, rab, es, fdr, hyp, pop, nbp = cModel._stats(counts[k], N)
+            ds["chr7-chr7-%d" % i] = {"distance": float(dist[k]), "ra": ra, "rb": rb, "rab": rab, "ES": es, "FDR": fdr, "hypergeometric_p-value": hyp,
+                                      "poisson_p-value": pop, "binomial_p-value": nbp, "iva": "chr7:%d-%d" % (cand[k, 0], cand[k, 1]),
+                                      "ivb": "chr7:%d-%d" % (cand[k, 2], cand[k, 3])}
+        ds = ns.cModel.removeDup(ds)
+        ds = ns.cModel.removeDup(ds) if len(ds) else ds
+        if len(ds) == 0:
+            assert got is None
+            continue
+        want = pd.DataFrame(ds).T
+        for col in ("poisson_p-value", "binomial_p-value", "hypergeometric_p-value"):
+            want[col + "_corrected"] = ns.cModel.getBonPvalues(want[col])
+        assert got.to_csv(sep="\t", index_label="loopId") == want.to_csv(sep="\t", index_label="loopId"), trial
+        assert ns.cModel.markIntSigHic(got.copy())["significant"].tolist() == ns.cModel.markIntSigHic(want.copy())["significant"].tolist()
+
+
 def test_nearby_windows_and_overlap():
     ivas, ivbs = cModel.getNearbyPairRegions([100, 301], [1000, 1400])
     assert len(ivas) == len(ivbs) == 10
