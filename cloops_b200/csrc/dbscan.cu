@@ -12,6 +12,7 @@
 //       adjacent cluster (only label -1 points are ever collected); a cluster with < minPts members is
 //       released (:180-185) and its points fall to later clusters; ids are dense over survivors.
 #include <limits.h>
+#include <stdlib.h>
 
 #include <cub/cub.cuh>
 #include <thrust/iterator/reverse_iterator.h>
@@ -19,6 +20,9 @@
 #include "index.cuh"
 
 namespace cloops {
+
+static const bool g_trace = getenv("CLOOPS_TRACE") != nullptr;
+static thread_local int g_trace_rounds = 0;
 
 enum : unsigned char { ST_NONE = 0, ST_ALIVE = 1, ST_DEAD = 2, ST_UNDECIDED = 3 };
 
@@ -550,11 +554,13 @@ int index_dbscan(cloops_index* ix, int minPts, int variant, int* d_labels, int* 
                 LAUNCH(v2_decide_kernel, cdiv(n_und, 256), 256, 0, st, W, n_und, minPts);
                 CU_TRY(cudaMemcpyAsync(counters, W.counters, sizeof(counters), cudaMemcpyDeviceToHost, st));
                 CU_TRY(cudaStreamSynchronize(st));
+                g_trace_rounds = round + 1;
                 if (counters[2] == 0) break;
                 if (round > na) return fail(CLOOPS_ECUDA, "v2 survival did not converge");
             }
             if (n_con > 0 && counters[3] > 0)
                 LAUNCH(v2_border_kernel<true>, cdiv(n_con, 256), 256, 0, st, ix->keys, ix->sstart, P, W, n_con);
+            if (g_trace) fprintf(stderr, "[cloops] v2 survival: n_act=%d undecided=%d contested=%d rounds=%d dead=%d\n", na, n_und, n_con, g_trace_rounds, counters[3]);
         }
         stage_mark("survival", st);
     }
