@@ -339,42 +339,51 @@ __global__ void __launch_bounds__(256) v2_reset_kernel(Work W, int n_und) {
 
 // lb(K): border points for which K is the lowest-ranked non-dead adjacent component (K's for sure if K lives)
 // ub(K): border points adjacent to K with no decided-alive adjacent component of lower rank
+// A border point is adjacent to at most NINE components: its neighbours lie in the 3 x 3 block of rotated floor cells
+// around it, and the core points of one cell are mutual neighbours (one component per cell, cDBSCAN2.py:80-83) -- so the
+// distinct adjacent components fit a fixed register list and every neighbour is looked at once.
+#define ADJ_MAX 9
 __global__ void __launch_bounds__(128) v2_accumulate_kernel(const u64* __restrict__ keys, const int* __restrict__ sstart,
                                                             GridParams P, Work W, int n_con) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_con) return;
     const int i = W.list_con[t];
     const PointView p = view(keys[i], P);
-    int min_nd_rank = INT_MAX, min_nd_root = -1, min_alive_rank = INT_MAX;
+    int roots[ADJ_MAX], ranks[ADJ_MAX];
+    unsigned undecided = 0;                     // bit k: roots[k] is undecided (else alive)
+    int n_adj = 0;
     RootCache rc;
     for_each_neighbour(keys, sstart, P, i, p, [&](int j, u64 kq) {
         if (!(kq >> 63)) return true;
+        const int before = rc.last_parent;
         rc.lookup(W, j);
-        const int r = rc.root, rk = rc.rank;
-        const unsigned char st = rc.status;
-        if (st == ST_DEAD) return true;
-        if (rk < min_nd_rank) { min_nd_rank = rk; min_nd_root = r; }
-        if (st == ST_ALIVE && rk < min_alive_rank) min_alive_rank = rk;
+        if (rc.last_parent == before) return true;          // same component as the previous core neighbour
+        if (rc.status == ST_DEAD) return true;
+        bool dup = false;
+#pragma unroll
+        for (int k = 0; k < ADJ_MAX; ++k) dup |= (k < n_adj && roots[k] == rc.root);
+        if (dup || n_adj >= ADJ_MAX) return true;
+#pragma unroll
+        for (int k = 0; k < ADJ_MAX; ++k)
+            if (k == n_adj) { roots[k] = rc.root; ranks[k] = rc.rank; }
+        undecided |= (rc.status == ST_UNDECIDED ? 1u : 0u) << n_adj;
+        ++n_adj;
         return true;
     });
-    if (min_nd_root < 0) return;
-    if (W.status[min_nd_root] == ST_UNDECIDED) atomicAdd(&W.size[min_nd_root], 1);
-    // every distinct undecided adjacent component ranked below the best alive one
-    RootCache rc2;
-    for_each_neighbour(keys, sstart, P, i, p, [&](int j, u64 kq) {
-        if (!(kq >> 63)) return true;
-        rc2.lookup(W, j);
-        const int r = rc2.root;
-        if (rc2.status != ST_UNDECIDED || rc2.rank >= min_alive_rank) return true;
-        bool first = true;                      // count each component once: only at its first visit
-        for_each_neighbour(keys, sstart, P, i, p, [&](int j2, u64 kq2) {
-            if (j2 == j) return false;
-            if ((kq2 >> 63) && root_of(W.parent, j2) == r) { first = false; return false; }
-            return true;
-        });
-        if (first) atomicAdd(&W.ub[r], 1);
-        return true;
-    });
+    int min_nd_rank = INT_MAX, min_nd = -1, min_alive_rank = INT_MAX;
+#pragma unroll
+    for (int k = 0; k < ADJ_MAX; ++k) {
+        if (k >= n_adj) continue;
+        if (ranks[k] < min_nd_rank) { min_nd_rank = ranks[k]; min_nd = k; }
+        if (!((undecided >> k) & 1u) && ranks[k] < min_alive_rank) min_alive_rank = ranks[k];
+    }
+    if (min_nd < 0) return;
+#pragma unroll
+    for (int k = 0; k < ADJ_MAX; ++k) {
+        if (k >= n_adj || !((undecided >> k) & 1u)) continue;
+        if (k == min_nd) atomicAdd(&W.size[roots[k]], 1);
+        if (ranks[k] < min_alive_rank) atomicAdd(&W.ub[roots[k]], 1);      // every distinct undecided component ranked below the best alive one
+    }
 }
 
 __global__ void __launch_bounds__(256) v2_decide_kernel(Work W, int n_und, int minPts) {

@@ -88,7 +88,15 @@ __global__ void __launch_bounds__(256) pack_kernel(const int* __restrict__ x, co
         u32 aux = (u32)i;
         if (cut > 0 && yy[k] - xx[k] < cut) {
             key = (u64)P.ns << P.sshift;                  // sentinel strip: sorts behind every active row
-            if (RANK) aux = (u32)atomicAdd(cnt_tail, 1);
+            if (RANK) {
+                // any distinct place in the tail will do (inactive rows are never looked at again): one atomic per warp,
+                // not one per row -- after the first round more than half of all rows are removed by the cut
+                const unsigned peers = __activemask();
+                const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+                int base = 0;
+                if (lane == leader) base = atomicAdd(cnt_tail, __popc(peers));
+                aux = (u32)(__shfl_sync(peers, base, leader) + __popc(peers & ((1u << lane) - 1)));
+            }
         } else {
             u32 up = (u32)((xx[k] - yy[k]) - P.ubase);
             u32 vp = (u32)((xx[k] + yy[k]) - P.vbase);

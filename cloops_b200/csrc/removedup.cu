@@ -88,3 +88,32 @@ extern "C" int cloops_remove_dup(const int64_t* a0, const int64_t* a1, const int
     *n_ties = nt;
     return 0;
 }
+
+// combineTwice (cLoops/pipe.py:155-174) over all clustering rounds of one chromosome at once.  rows int32[n,4] = the
+// inter-ligation candidates (minX, maxX, minY, maxY) of every round, concatenated in round order; round int32[n] = the
+// round each row came from (non-decreasing).  keep[i] = 0 iff the exact same box was already produced by an EARLIER round
+// (boxes repeated inside one round are all kept, as the reference keeps them).  One pass over an open-addressing table.
+extern "C" int cloops_combine_rounds(const int32_t* rows, const int32_t* round, int64_t n, uint8_t* keep) {
+    using cloops::fail;
+    if (n < 0 || (n > 0 && (!rows || !round || !keep))) return fail(CLOOPS_EINVAL, "bad argument");
+    if (n == 0) return 0;
+    size_t cap = 16;
+    while (cap < (size_t)n * 2) cap <<= 1;
+    std::vector<int64_t> slot(cap, -1);                        // index of the first row holding the box
+    const size_t mask = cap - 1;
+    for (int64_t i = 0; i < n; ++i) {
+        const int32_t* r = rows + 4 * i;
+        uint64_t h = ((uint64_t)(uint32_t)r[0] << 32 | (uint32_t)r[1]) * 0x9E3779B97F4A7C15ull;
+        h ^= ((uint64_t)(uint32_t)r[2] << 32 | (uint32_t)r[3]) * 0xC2B2AE3D27D4EB4Full;
+        h ^= h >> 29;
+        size_t at = (size_t)h & mask;
+        for (;;) {
+            const int64_t j = slot[at];
+            if (j < 0) { slot[at] = i; keep[i] = 1; break; }
+            const int32_t* q = rows + 4 * j;
+            if (q[0] == r[0] && q[1] == r[1] && q[2] == r[2] && q[3] == r[3]) { keep[i] = round[j] == round[i]; break; }
+            at = (at + 1) & mask;
+        }
+    }
+    return 0;
+}

@@ -77,16 +77,15 @@ __global__ void __launch_bounds__(256) dist_stats_kernel(const int* __restrict__
 }
 
 // mom: 0 n_i, 1 S_i, 2 Q_i, 3 n_s, 4 S_s, 5 Q_s, 6 len(dis), 7 len(dss), 8 chromosomes with inter-ligation clusters
-__global__ void __launch_bounds__(32) dist_stats_commit_kernel(const double* __restrict__ partial, int nblocks, const int* __restrict__ n_inter,
-                                                               double* __restrict__ mom) {
+__global__ void __launch_bounds__(32 * RS_NQ) dist_stats_commit_kernel(const double* __restrict__ partial, int nblocks, const int* __restrict__ n_inter,
+                                                                       double* __restrict__ mom) {
     if (*n_inter == 0) return;
-    const int k = threadIdx.x;
-    if (k < RS_NQ) {
-        double v = 0;
-        for (int b = 0; b < nblocks; ++b) v += partial[b * RS_NQ + k];
-        mom[k] += v;
-    }
-    if (k == RS_NQ) mom[8] += 1.0;
+    const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;       // one warp per quantity; fixed summation order
+    double v = 0;
+    for (int b = lane; b < nblocks; b += 32) v += partial[b * RS_NQ + k];
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    if (lane == 0) mom[k] += v;
+    if (threadIdx.x == 0) mom[8] += 1.0;
 }
 
 // the two middle order statistics of the histogrammed values: out[0] = value of rank (k-1)/2, out[1] = value of rank k/2
@@ -125,7 +124,7 @@ int pass_distance_stats(const int* xs, const int* ys, const unsigned char* membe
     CU_TRY(cudaMemsetAsync(d_ninter, 0, sizeof(int), st));
     if (k > 0) LAUNCH(count_inter_kernel, cdiv(k, 256), 256, 0, st, kind, k, d_ninter);
     LAUNCH(dist_stats_kernel, RS_GRID, 256, 0, st, xs, ys, member_kind, n_members, raw_x, raw_y, n_raw, cut, d_ninter, d_hist, d_partial);
-    LAUNCH(dist_stats_commit_kernel, 1, 32, 0, st, d_partial, RS_GRID, d_ninter, d_mom);
+    LAUNCH(dist_stats_commit_kernel, 1, 32 * RS_NQ, 0, st, d_partial, RS_GRID, d_ninter, d_mom);
     return 0;
 }
 

@@ -229,21 +229,15 @@ def _round(fs, eps, minPts, cut, weights=None):
 
 def _combine_rounds(rounds):
     """combineTwice (pipe.py:155-174) over all rounds of one chromosome at once: a record is dropped iff the exact same
-    bbox was produced by an EARLIER round; order = round order, then cluster id.  rounds: list of int [K,4] arrays."""
+    bbox was produced by an EARLIER round; order = round order, then cluster id.  rounds: list of int32 [K,4] arrays.
+    The membership test runs in host C++ (``cloops_combine_rounds``: one pass over a hash table)."""
     if len(rounds) == 1:
         return rounds[0]
-    allr = np.concatenate(rounds)
-    rnd = np.repeat(np.arange(len(rounds)), [len(r) for r in rounds])
-    a = allr.astype(np.int64)
-    k1 = (a[:, 0] << 32) | (a[:, 1] & 0xffffffff)
-    k2 = (a[:, 2] << 32) | (a[:, 3] & 0xffffffff)
-    order = np.lexsort((rnd, k2, k1))
-    sk1, sk2, srnd = k1[order], k2[order], rnd[order]
-    head = np.r_[True, (sk1[1:] != sk1[:-1]) | (sk2[1:] != sk2[:-1])]
-    first = srnd[np.flatnonzero(head)][np.cumsum(head) - 1]        # earliest round of each distinct bbox
-    keep = np.empty(len(allr), bool)
-    keep[order] = srnd == first
-    return allr[keep]
+    allr = np.ascontiguousarray(np.concatenate(rounds), dtype=np.int32)
+    rnd = np.ascontiguousarray(np.repeat(np.arange(len(rounds), dtype=np.int32), [len(r) for r in rounds]))
+    keep = np.empty(len(allr), np.uint8)
+    _lib.check(_lib.lib().cloops_combine_rounds(allr.ctypes.data, rnd.ctypes.data, len(allr), keep.ctypes.data))
+    return allr[keep.view(bool)]
 
 
 def _rounds(cfs, eps, minPts, cut, max_cut, log, weights=None):

@@ -176,6 +176,10 @@ CLOOPS_API int cloops_remove_dup(const int64_t* a0, const int64_t* a1, const int
                       const double* dens, int64_t n, double bpcut, int64_t* keep, int64_t* n_keep, int64_t* tie_start,
                       int64_t* tie_members, int64_t* n_ties);
 
+/* combineTwice (cLoops/pipe.py:155-174) over all clustering rounds of one chromosome at once: rows int32[n,4] = candidate
+ * boxes of every round in round order, round int32[n]; keep u8[n] = 0 iff the same box came from an EARLIER round.  Host C++. */
+CLOOPS_API int cloops_combine_rounds(const int32_t* rows, const int32_t* round, int64_t n, uint8_t* keep);
+
 #ifdef __cplusplus
 }
 #endif
