@@ -6,6 +6,8 @@
 // restricted to u in [u-eps, u+eps]); inside the own strip |dv| <= eps-1 holds by construction, in strip s-1 (s+1) the
 // remaining test is vmod_q >= vmod_p (vmod_q <= vmod_p).
 #include <limits.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include <type_traits>
 
@@ -346,6 +348,268 @@ __global__ void __launch_bounds__(CT_THREADS) count_kernel_tiled(const u64* __re
     }
 }
 
+
+// --------------------------------------------------------------------------------------------------
+// Region query, split form (round 2; the production kernel -- count_kernel_tiled above is kept for A/B runs,
+// CLOOPS_RQ=tiled).  Same tile, same W words and guards as above; what changes is how the work after the own strip
+// is organised, because in the tiled form every warp paid for the widest case of any of its lanes:
+//  * vmod is staged as 16-bit words (tiles with eps > 65536 take the global walk), the strip table as 16-bit slots:
+//    25 KB of shared memory per CTA with the two queues below.
+//  * phase 1 (own strip) as before for the templated caps; for caps >= 10 and exact counts the four nearest points on
+//    each side are register compares as well, then three saturation probes (the cap-1 nearest points to the left, to the
+//    right, and split around the point) settle the dense Hi-C diagonal in a handful of loads, and only points whose
+//    window reaches further scan on -- instead of two full uniform searches per point.
+//  * phase 2a: the unsaturated points (queue Q1) run the two uniform lower-bound searches and ONE load each to see
+//    whether the window in strip s-1 / s+1 holds anything at all (73 % do not at ChIA-PET density).  Non-empty
+//    windows are compacted into a second queue Q2 (point, slot of the first word, direction).
+//  * phase 2b: one thread per non-empty window walks it with the v test and adds to the point's count (shared atomic on
+//    the Q1 entry).  Only points that met a non-empty window rewrite their count (phase 3).
+// The uniform search is a straight ladder selected once per CTA by the tile's step count.
+#define CQ_V16_BITS 16
+
+__device__ __forceinline__ u32 lds_u16(u32 a) {
+    unsigned short v;
+    asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+    return v;
+}
+
+#define CQ_STEP_CLAMPED(SB)                                   \
+    {                                                         \
+        const u32 na = min(pa + (SB), last_a);                \
+        if (lds_off<0>(na) < t) pa = na;                      \
+    }
+// as uniform_lower_bound, the halving steps unrolled into a ladder entered at the tile's step count
+__device__ __forceinline__ u32 ladder_lower_bound(u32 pa, u32 t, int nsteps, u32 last_a) {
+    switch (nsteps) {                                          // CTA-uniform
+        default:
+#pragma unroll 1
+            for (u32 sb = 2u << nsteps; sb > 4096u; sb >>= 1) CQ_STEP_CLAMPED(sb)
+        case 11: CQ_STEP_CLAMPED(4096u)
+        case 10: CQ_STEP_CLAMPED(2048u)
+        case 9: CQ_STEP_CLAMPED(1024u)
+        case 8: CQ_STEP_CLAMPED(512u)
+        case 7: CQ_STEP_CLAMPED(256u)
+        case 6: CQ_STEP_CLAMPED(128u)
+        case 5: CQ_STEP_CLAMPED(64u)
+        case 4: case 3: case 2: case 1: case 0: break;
+    }
+    if (lds_off<32>(pa) < t) pa += 32u;
+    if (lds_off<16>(pa) < t) pa += 16u;
+    if (lds_off<8>(pa) < t) pa += 8u;
+    if (lds_off<4>(pa) < t) pa += 4u;
+    return pa + 4u;
+}
+
+template <int CAPT>
+__global__ void __launch_bounds__(CT_THREADS) count_kernel_split(const u64* __restrict__ keys, const int* __restrict__ sstart,
+                                                                 const TileInfo* __restrict__ tiles, GridParams P, int cap_rt,
+                                                                 int* __restrict__ cnt, int vec_ok) {
+    constexpr int RMAX = CT_RMAX;
+    constexpr int NP = CAPT > 0 ? CAPT - 1 : 4;                          // register probes on each side
+    constexpr int NV = NP > 4 ? 2 : 1;                                   // 128-bit words of context on each side
+    __shared__ __align__(16) u32 Wg[RMAX + CT_G + 12 + 4];
+    __shared__ __align__(16) unsigned short Vg[RMAX + CT_G + 12 + 4];
+    __shared__ __align__(16) u32 Q1[CT_TILE];                            // point | dirty << 10 | count << 12
+    __shared__ u32 Q2[2 * CT_TILE];                                      // Q1 index | slot << 10 | direction << 22
+    __shared__ unsigned short S[CT_SMAX];
+    __shared__ int s_nq1, s_nq2;
+    const int cap = CAPT > 0 ? CAPT : cap_rt;
+    const int tid = threadIdx.x;
+    const int t0 = blockIdx.x * CT_TILE;
+    const int t1 = min(t0 + CT_TILE, P.n_act);
+    const int4 ti = __ldg(reinterpret_cast<const int4*>(tiles) + blockIdx.x);
+    const int sA = ti.x, r0 = ti.y, r1 = ti.z, nse = ti.w & 0xffff, nsteps = ti.w >> 16;
+    if (nse == 0) {                               // CTA-uniform: the staged range does not fit
+        for (int i = t0 + tid; i < t1; i += CT_THREADS) cnt[i] = count_point_global(keys, sstart, P, cap, i);
+        return;
+    }
+    const int be = P.be, bu = P.bu;
+    const u32 eps = (u32)P.eps, one = 1u << bu, emask = P.emask;
+    const int sl0 = CT_G - (r0 & ~3);             // slot of global index j = sl0 + j ; slot % 4 == j % 4
+    if (tid == 0) { s_nq1 = 0; s_nq2 = 0; }
+    {
+        const u32 base = (u32)((long long)(sA - 1) << bu);      // strip sA-1 -> relative strip 0 (mod 2^32)
+        const ulonglong2* __restrict__ k2 = reinterpret_cast<const ulonglong2*>(keys);
+        const int p_hi = r1 >> 1;
+        const int j2 = ((r0 + 1) >> 1) + tid;                   // whole key pairs inside [r0, r1)
+        auto put = [&](int j, const ulonglong2& kk) {
+            const int sl = sl0 + 2 * j;                         // even
+            *reinterpret_cast<uint2*>(&Wg[sl]) = make_uint2((u32)(kk.x >> be) - base, (u32)(kk.y >> be) - base);
+            *reinterpret_cast<u32*>(&Vg[sl]) = ((u32)kk.x & emask) | (((u32)kk.y & emask) << 16);
+        };
+        ulonglong2 kk[3];                                       // all loads of the common case in flight at once
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            if (j2 + k * CT_THREADS < p_hi) kk[k] = __ldg(k2 + j2 + k * CT_THREADS);
+#pragma unroll 1
+        for (int k = tid; k < nse; k += CT_THREADS) S[k] = (unsigned short)(__ldg(sstart + sA + k) + sl0);   // strip offsets as slots
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            if (j2 + k * CT_THREADS < p_hi) put(j2 + k * CT_THREADS, kk[k]);
+#pragma unroll 1
+        for (int j = j2 + 3 * CT_THREADS; j < p_hi; j += CT_THREADS) put(j, __ldg(k2 + j));
+        if (tid >= 64 && tid < 66) {                            // the unpaired first / last point
+            const int j = tid == 64 ? r0 : r1 - 1;
+            if (j & 1 ? tid == 64 : tid == 65) {
+                const u64 k = __ldg(keys + j);
+                Wg[sl0 + j] = (u32)(k >> be) - base;
+                Vg[sl0 + j] = (unsigned short)((u32)k & emask);
+            }
+        }
+        if (tid >= 128 && tid < 128 + CT_G) Wg[sl0 + r0 - 1 - (tid - 128)] = 0u;
+        if (tid >= 160 && tid < 160 + 12) Wg[sl0 + r1 + (tid - 160)] = 0xffffffffu;
+    }
+    __syncthreads();
+    const u32 w_a = (u32)__cvta_generic_to_shared(Wg);          // shared byte addresses
+    const u32 v_a = (u32)__cvta_generic_to_shared(Vg);
+    const u32 q1_a = (u32)__cvta_generic_to_shared(Q1);
+    const u32 first_a = w_a + 4u * (u32)(sl0 + r0 - CT_G);      // first left guard word
+    const u32 last_a = w_a + 4u * (u32)(sl0 + r1);              // first right guard word
+    const int lane = tid & 31;
+    // ---- phase 1: own strip, four consecutive points per thread; saturated counts are final
+    const int i0 = t0 + 4 * tid;
+    {
+        unsigned nm = 0;                                                 // bit k: point k is not saturated yet
+        int c[4] = {0, 0, 0, 0};
+        if (i0 < t1) {
+            const int s0 = sl0 + i0;                                     // multiple of 4
+            u32 w[4 * (2 * NV + 1)];
+#pragma unroll
+            for (int v = 0; v < 2 * NV + 1; ++v) {
+                const uint4 x = *reinterpret_cast<const uint4*>(&Wg[s0 + 4 * (v - NV)]);
+                w[4 * v] = x.x; w[4 * v + 1] = x.y; w[4 * v + 2] = x.z; w[4 * v + 3] = x.w;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const u32 wp = w[4 * NV + k];
+                const u32 lo = wp - eps, hi = wp + eps;
+                int cc = 1;
+                if (CAPT > 0) {
+#pragma unroll
+                    for (int q = 1; q <= NP; ++q) {
+                        inc_ge(cc, w[4 * NV + k - q], lo);
+                        inc_le(cc, w[4 * NV + k + q], hi);
+                    }
+                } else {
+                    int cl = 0, cr = 0;
+#pragma unroll
+                    for (int q = 1; q <= NP; ++q) {
+                        inc_ge(cl, w[4 * NV + k - q], lo);
+                        inc_le(cr, w[4 * NV + k + q], hi);
+                    }
+                    cc = 1 + cl + cr;
+                    if ((cl == NP || cr == NP) && cc < cap && i0 + k < t1) {         // the window reaches past the register probes
+                        const int pa = (int)(w_a + 4u * (u32)(s0 + k));
+                        if (cap <= 0x10000) {                                        // saturation probes: cap-1 nearest on one side, or split
+                            const int far = 4 * (cap - 1), ha = 4 * ((cap - 1) >> 1), hb = far - ha;
+                            const bool sat = lds_off<0>((u32)max(pa - far, (int)first_a)) >= lo || lds_off<0>((u32)min(pa + far, (int)last_a)) <= hi ||
+                                             (lds_off<0>((u32)max(pa - ha, (int)first_a)) >= lo && lds_off<0>((u32)min(pa + hb, (int)last_a)) <= hi);
+                            if (sat) cc = cap;
+                        }
+                        if (cc < cap && cl == NP)
+                            for (u32 a = (u32)pa - 4u * (NP + 1); cc < cap && lds_off<0>(a) >= lo; a -= 4u) ++cc;
+                        if (cc < cap && cr == NP)
+                            for (u32 a = (u32)pa + 4u * (NP + 1); cc < cap && lds_off<0>(a) <= hi; a += 4u) ++cc;
+                    }
+                }
+                c[k] = cc;
+                nm |= (cc < cap && i0 + k < t1) ? (1u << k) : 0u;
+            }
+            const int4 r = make_int4(min(c[0], cap), min(c[1], cap), min(c[2], cap), min(c[3], cap));
+            if (vec_ok && i0 + 3 < t1) {
+                *reinterpret_cast<int4*>(cnt + i0) = r;
+            } else {
+                cnt[i0] = r.x;
+                if (i0 + 1 < t1) cnt[i0 + 1] = r.y;
+                if (i0 + 2 < t1) cnt[i0 + 2] = r.z;
+                if (i0 + 3 < t1) cnt[i0 + 3] = r.w;
+            }
+        }
+        // ---- queue of the points whose own strip did not saturate them (warp scan of the per-thread counts)
+        const int mine = __popc(nm);
+        int incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += y;
+        }
+        const int tot = __shfl_sync(0xffffffffu, incl, 31);
+        if (tot) {                                                       // warp-uniform
+            int qb = 0;
+            if (lane == 0) qb = atomicAdd(&s_nq1, tot);
+            qb = __shfl_sync(0xffffffffu, qb, 0) + incl - mine;
+            u32 qa = q1_a + 4u * (u32)qb;                                // running store address
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const u32 e = (u32)(4 * tid + k) | ((u32)c[k] << 12);
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p st.shared.u32 [%0], %2;\n\t@p add.u32 %0, %0, 4;\n\t}"
+                             : "+r"(qa) : "r"(nm & (1u << k)), "r"(e) : "memory");
+            }
+        }
+    }
+    __syncthreads();
+    // ---- phase 2a: both lower bounds of every queued point; non-empty windows go to Q2
+    const int nq1 = s_nq1;
+    if (nq1 == 0) return;                                                // CTA-uniform
+    {
+        const u32 s_a = (u32)__cvta_generic_to_shared(S);
+        const unsigned lt = (1u << lane) - 1u;
+#pragma unroll 1
+        for (int q0 = 0; q0 < nq1; q0 += CT_THREADS) {
+            const int q = q0 + tid;
+            const bool live = q < nq1;
+            const u32 e = live ? Q1[q] : 0u;
+            const u32 pa = w_a + 4u * (u32)(sl0 + t0 + (int)(e & 1023u));
+            const u32 wp = lds_off<0>(pa);
+            const u32 sr = s_a + 2u * (wp >> bu);                        // address of S[srel]
+            const u32 ja = ladder_lower_bound(w_a + 4u * lds_u16(sr - 2u) - 4u, wp - one - eps, nsteps, last_a);
+            const u32 jb = ladder_lower_bound(w_a + 4u * lds_u16(sr + 2u) - 4u, wp + one - eps, nsteps, last_a);
+            const bool hit0 = live && lds_off<0>(ja) <= wp - one + eps;
+            const bool hit1 = live && lds_off<0>(jb) <= wp + one + eps;
+            const unsigned b0 = __ballot_sync(0xffffffffu, hit0), b1 = __ballot_sync(0xffffffffu, hit1);
+            const int n0 = __popc(b0), tot = n0 + __popc(b1);
+            if (tot) {                                                   // warp-uniform
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&s_nq2, tot);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (hit0) Q2[base + __popc(b0 & lt)] = (u32)q | (((ja - w_a) >> 2) << 10);
+                if (hit1) Q2[base + n0 + __popc(b1 & lt)] = (u32)q | (((jb - w_a) >> 2) << 10) | (1u << 22);
+                if (hit0 || hit1) Q1[q] = e | 1024u;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- phase 2b: one thread per non-empty window: v test on every point of the window, stopping once the point is saturated
+    const int nq2 = s_nq2;
+    if (nq2 == 0) return;                                                // CTA-uniform
+#pragma unroll 1
+    for (int x = tid; x < nq2; x += CT_THREADS) {
+        const u32 e2 = Q2[x];
+        const u32 qi = e2 & 1023u;
+        u32 i = (e2 >> 10) & 4095u;
+        const bool next = (e2 >> 22) != 0u;
+        const u32 e1 = *reinterpret_cast<volatile u32*>(&Q1[qi]);
+        const u32 slot = (u32)(sl0 + t0) + (e1 & 1023u);
+        const u32 wp = lds_off<0>(w_a + 4u * slot), vm = lds_u16(v_a + 2u * slot);
+        const u32 thi = next ? wp + one + eps : wp - one + eps;
+        const int room = cap - (int)(e1 >> 12);
+        int f = 0;
+        do {
+            const u32 v = lds_u16(v_a + 2u * i);
+            f += (next ? v <= vm : v >= vm) ? 1 : 0;
+            ++i;
+        } while (f < room && lds_off<0>(w_a + 4u * i) <= thi);
+        if (f) atomicAdd(&Q1[qi], (u32)f << 12);
+    }
+    __syncthreads();
+    // ---- phase 3: the points that met a non-empty window rewrite their count
+#pragma unroll 1
+    for (int q = tid; q < nq1; q += CT_THREADS) {
+        const u32 e = Q1[q];
+        if (e & 1024u) cnt[t0 + (int)(e & 1023u)] = min((int)(e >> 12), cap);
+    }
+}
+
 template <int RMAX>
 static int launch_count_tiled(const cloops_index* ix, int cap, int* out, cudaStream_t st) {
     const GridParams& P = ix->P;
@@ -361,6 +625,19 @@ static int launch_count_tiled(const cloops_index* ix, int cap, int* out, cudaStr
     return 0;
 }
 
+static int launch_count_split(const cloops_index* ix, int cap, int* out, cudaStream_t st) {
+    const GridParams& P = ix->P;
+    const int grid = cdiv(P.n_act, CT_TILE);
+    const int vec_ok = (((uintptr_t)out) & 15) == 0 ? 1 : 0;
+    const TileInfo* tiles = reinterpret_cast<const TileInfo*>(ix->tiles);
+    switch (cap) {
+#define CQ_CASE(C) case C: LAUNCH((count_kernel_split<C>), grid, CT_THREADS, 0, st, ix->keys, ix->sstart, tiles, P, cap, out, vec_ok); break;
+        CQ_CASE(2) CQ_CASE(3) CQ_CASE(4) CQ_CASE(5) CQ_CASE(6) CQ_CASE(7) CQ_CASE(8) CQ_CASE(9)
+#undef CQ_CASE
+        default: LAUNCH((count_kernel_split<0>), grid, CT_THREADS, 0, st, ix->keys, ix->sstart, tiles, P, cap, out, vec_ok); break;
+    }
+    return 0;
+}
 
 // per-tile headers of an index (called once by index_build)
 int index_tiles(cloops_index* ix, cudaStream_t st) {
@@ -376,7 +653,9 @@ int index_count(cloops_index* ix, int cap, int* d_counts_sorted, cudaStream_t st
     const GridParams& P = ix->P;
     if (P.n_act == 0) return 0;
     if (cap <= 0) cap = INT_MAX;
-    return launch_count_tiled<CT_RMAX>(ix, cap, d_counts_sorted, st);
+    static const bool use_tiled = getenv("CLOOPS_RQ") != nullptr && strcmp(getenv("CLOOPS_RQ"), "tiled") == 0;   // A/B knob
+    if (use_tiled || P.be > CQ_V16_BITS) return launch_count_tiled<CT_RMAX>(ix, cap, d_counts_sorted, st);
+    return launch_count_split(ix, cap, d_counts_sorted, st);
 }
 
 }  // namespace cloops

@@ -392,7 +392,7 @@ def call_loops(cfs, eps, minPts, hic=0, cut=0, max_cut=False, weights=None, tail
         return out
     # the statistics tail of one chromosome (host threads) runs while the GPU counts the next one
     from concurrent.futures import ThreadPoolExecutor
-    with ThreadPoolExecutor(max_workers=1) as ex:
+    with ThreadPoolExecutor(max_workers=max(1, min(6, (os.cpu_count() or 2) // 2))) as ex:
         futs = {k: ex.submit(cModel.tableFromCounts, cModel.countCandidates(dataI[k]["f"], dataI[k]["records"], minPts, 0)) for k in dataI}
         tables = {k: f.result() for k, f in futs.items()}
     ds = _tables(dataI, tables, _local=True, done=True)
