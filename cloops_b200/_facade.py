@@ -14,6 +14,17 @@ from . import device
 from ._lib import CloopsError
 
 
+def _close_gaps(c, eps: int):
+    """Order-preserving re-coding of one coordinate axis: differences <= eps are kept exactly, larger gaps between
+    consecutive distinct values become eps + 1, the smallest value becomes 0."""
+    c = np.asarray(c, dtype=np.int64)
+    order = np.argsort(c, kind="stable")
+    s = c[order]
+    out = np.empty_like(c)
+    out[order] = np.concatenate([[0], np.cumsum(np.minimum(np.diff(s), eps + 1))])
+    return out
+
+
 class _GpuDBSCAN:
     _variant = None
 
@@ -36,8 +47,15 @@ class _GpuDBSCAN:
             self.labels_array = np.zeros(0, np.int32)
             self.info = {}
             return
-        dx = device.to_device_i32(mat[:, 1], "X")
-        dy = device.to_device_i32(mat[:, 2], "Y")
+        X, Y = mat[:, 1], mat[:, 2]
+        if self._variant == 1 and n and (max(abs(int(X.min())), abs(int(X.max())), abs(int(Y.min())), abs(int(Y.max()))) >= device.COORD_LIMIT):
+            # scripts/callStripes:42-43 scales one axis by 50 before clustering with the v1 class: coordinates beyond int32.
+            # v1's labels depend on the Manhattan neighbour relation and on row order only (its grid offset is
+            # label-neutral), and that relation survives shrinking every gap between consecutive distinct values of an axis
+            # that is wider than eps down to eps + 1 -- so sparse wide-range inputs are folded back into int32.
+            X, Y = _close_gaps(X, int(eps)), _close_gaps(Y, int(eps))
+        dx = device.to_device_i32(X, "X")
+        dy = device.to_device_i32(Y, "Y")
         lab, self.info = device.dbscan_device(dx, dy, int(eps), int(minPts), self._variant)
         self.labels_array = lab.cpu().numpy()
 

@@ -32,36 +32,131 @@ __device__ __forceinline__ void extents_point(int xx, int yy, int cut, int& umin
     ++cnt;
 }
 
-// vec: x and y are 16-byte aligned -> four rows per 128-bit load
+// Rows are looked at in tiles of 1024 consecutive rows (four per thread, one 128-bit load each when x and y are 16-byte
+// aligned); the number of a tile's rows that pass the cut filter goes to blockcnt[tile] -- the input of the stable compaction
+// below.  A CTA takes EX_TILES consecutive tiles, so the five global atomics of the extents are paid once per 8192 rows.
+#define EX_ROWS 1024
+#define EX_TILES 8
 __global__ void __launch_bounds__(256) extents_kernel(const int* __restrict__ x, const int* __restrict__ y, int n, int cut, int vec,
-                                                      Extents* out) {
-    int umin = INT_MAX, umax = INT_MIN, vmin = INT_MAX, vmax = INT_MIN, cnt = 0, bad = 0;
-    const int stride = gridDim.x * blockDim.x, t = blockIdx.x * blockDim.x + threadIdx.x;
-    int done = 0;
-    if (vec) {
-        const int n4 = n >> 2;
-        const int4* __restrict__ x4 = reinterpret_cast<const int4*>(x);
-        const int4* __restrict__ y4 = reinterpret_cast<const int4*>(y);
-        for (int i = t; i < n4; i += stride) {
-            const int4 a = __ldg(x4 + i), b = __ldg(y4 + i);
+                                                      Extents* out, int* __restrict__ blockcnt) {
+    __shared__ int s_cnt[8];
+    __shared__ int s_ext[8][4];
+    int umin = INT_MAX, umax = INT_MIN, vmin = INT_MAX, vmax = INT_MIN, bad = 0, total = 0;
+    const int ntile = (n + EX_ROWS - 1) / EX_ROWS;
+    for (int tile = blockIdx.x * EX_TILES; tile < min((int)(blockIdx.x + 1) * EX_TILES, ntile); ++tile) {
+        int cnt = 0;
+        const int i0 = tile * EX_ROWS + 4 * threadIdx.x;
+        if (vec && i0 + 3 < n) {
+            const int4 a = __ldg(reinterpret_cast<const int4*>(x + i0)), b = __ldg(reinterpret_cast<const int4*>(y + i0));
             extents_point(a.x, b.x, cut, umin, umax, vmin, vmax, cnt, bad);
             extents_point(a.y, b.y, cut, umin, umax, vmin, vmax, cnt, bad);
             extents_point(a.z, b.z, cut, umin, umax, vmin, vmax, cnt, bad);
             extents_point(a.w, b.w, cut, umin, umax, vmin, vmax, cnt, bad);
+        } else {
+            for (int i = i0; i < min(i0 + 4, n); ++i) extents_point(__ldg(x + i), __ldg(y + i), cut, umin, umax, vmin, vmax, cnt, bad);
         }
-        done = n4 << 2;
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = cnt;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0;
+            for (int w = 0; w < 8; ++w) tot += s_cnt[w];
+            blockcnt[tile] = tot;
+            total += tot;
+        }
+        __syncthreads();
     }
-    for (int i = done + t; i < n; i += stride) extents_point(__ldg(x + i), __ldg(y + i), cut, umin, umax, vmin, vmax, cnt, bad);
     if (bad) out->overflow = 1;
     umin = __reduce_min_sync(0xffffffffu, umin);
     umax = __reduce_max_sync(0xffffffffu, umax);
     vmin = __reduce_min_sync(0xffffffffu, vmin);
     vmax = __reduce_max_sync(0xffffffffu, vmax);
-    cnt = __reduce_add_sync(0xffffffffu, cnt);
-    if ((threadIdx.x & 31) == 0 && cnt > 0) {
+    if ((threadIdx.x & 31) == 0) {
+        int* e = s_ext[threadIdx.x >> 5];
+        e[0] = umin; e[1] = umax; e[2] = vmin; e[3] = vmax;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && total > 0) {
+        for (int w = 0; w < 8; ++w) {
+            umin = min(umin, s_ext[w][0]); umax = max(umax, s_ext[w][1]); vmin = min(vmin, s_ext[w][2]); vmax = max(vmax, s_ext[w][3]);
+        }
         atomicMin(&out->umin, umin); atomicMax(&out->umax, umax);
         atomicMin(&out->vmin, vmin); atomicMax(&out->vmax, vmax);
-        atomicAdd(&out->n_act, cnt);
+        atomicAdd(&out->n_act, total);
+    }
+}
+
+// exclusive scan of the per-CTA counts, in place (one CTA; m = rows / 1024 entries)
+__global__ void __launch_bounds__(1024) blockcnt_scan_kernel(int* __restrict__ a, int m) {
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < m; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < m ? a[i] : 0;
+        int incl = v;
+        for (int d = 1; d < 32; d <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, incl, d);
+            if ((threadIdx.x & 31) >= d) incl += y;
+        }
+        if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int w = s_warp[threadIdx.x];
+            for (int d = 1; d < 32; d <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, w, d);
+                if ((int)threadIdx.x >= d) w += y;
+            }
+            s_warp[threadIdx.x] = w;
+        }
+        __syncthreads();
+        const int before = s_carry + (threadIdx.x >= 32 ? s_warp[(threadIdx.x >> 5) - 1] : 0) + incl - v;
+        if (i < m) a[i] = before;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = before + v;
+        __syncthreads();
+    }
+}
+
+// Keys of the rows that pass the cut filter only, compacted in ROW ORDER (stable): position = rows of earlier CTAs
+// (blockbase, the scanned counts of extents_kernel) + earlier active rows of this CTA.  The radix sort then moves n_act
+// rows instead of n -- after the first round of a Hi-C run the cut removes more than half of them.
+__global__ void __launch_bounds__(256) pack_compact_kernel(const int* __restrict__ x, const int* __restrict__ y, int cut, GridParams P,
+                                                           const int* __restrict__ blockbase, u64* __restrict__ keys,
+                                                           u32* __restrict__ rows) {
+    __shared__ int s_warp[8];
+    const int i0 = blockIdx.x * EX_ROWS + 4 * threadIdx.x;
+    u64 key[4];
+    unsigned act = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = i0 + k;
+        if (i >= P.n) continue;
+        const int xx = __ldg(x + i), yy = __ldg(y + i);
+        if (yy - xx < cut) continue;
+        const u32 up = (u32)((xx - yy) - P.ubase), vp = (u32)((xx + yy) - P.vbase);
+        const u32 sv = vp / (u32)P.eps, vm = vp - sv * (u32)P.eps;
+        key[k] = ((u64)sv << P.sshift) | ((u64)up << P.be) | (u64)vm;
+        act |= 1u << k;
+    }
+    const int mine = __popc(act), lane = threadIdx.x & 31;
+    int incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    if (lane == 31) s_warp[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    int pos = blockbase[blockIdx.x] + incl - mine;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) pos += s_warp[w];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (!(act & (1u << k))) continue;
+        keys[pos] = key[k];
+        rows[pos] = (u32)(i0 + k);
+        ++pos;
     }
 }
 
@@ -297,11 +392,13 @@ int index_build(const int32_t* d_x, const int32_t* d_y, int64_t n, int32_t eps, 
 
     Temp tmp(st);
     Extents* d_ext;
+    int* d_blockcnt;
+    const int nblk = cdiv(n, EX_ROWS);
     RET_IF(tmp.alloc(&d_ext, 1));
+    RET_IF(tmp.alloc(&d_blockcnt, nblk));
     LAUNCH(extents_init_kernel, 1, 1, 0, st, d_ext);
-    int grid = std::min(cdiv(n, 256), 148 * 8);
     const int vec = ((((uintptr_t)d_x) | ((uintptr_t)d_y)) & 15) == 0 ? 1 : 0;
-    LAUNCH(extents_kernel, grid, 256, 0, st, d_x, d_y, (int)n, cut, vec, d_ext);
+    LAUNCH(extents_kernel, cdiv(nblk, EX_TILES), 256, 0, st, d_x, d_y, (int)n, cut, vec, d_ext, d_blockcnt);
     Extents ext;
     CU_TRY(cudaMemcpyAsync(&ext, d_ext, sizeof(ext), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
@@ -355,7 +452,10 @@ int index_build(const int32_t* d_x, const int32_t* d_y, int64_t n, int32_t eps, 
     const char* knob = getenv("CLOOPS_INDEX_SORT");                                       // test / measurement knob
     const bool force_radix = knob != nullptr && strcmp(knob, "radix") == 0;
     const bool force_count = knob != nullptr && strcmp(knob, "count") == 0;
-    if (!force_radix && (long long)P.ns <= 4LL * P.n_act + 1024) {
+    // long strips (Hi-C density: more than ~50 rows per strip on average) go to the radix sort at once: the histogram and
+    // arrival ranks of the counting attempt would be thrown away (measured break-even ~ 80 rows per strip, see below)
+    const bool long_strips = (long long)P.n_act > 48LL * P.ns;
+    if (!force_radix && (force_count || !long_strips) && (long long)P.ns <= 4LL * P.n_act + 1024) {
         u64* k2;
         u32* r2;
         unsigned long long* d_sumsq;
@@ -402,13 +502,20 @@ int index_build(const int32_t* d_x, const int32_t* d_y, int64_t n, int32_t eps, 
         counted = true;
     }
     if (!counted) {
-        LAUNCH(pack_kernel<false>, cdiv(n, 1024), 256, 0, st, d_x, d_y, cut, P, k0, r0, (int*)nullptr, (int*)nullptr);
+        int n_sort = (int)n;
+        if (cut > 0 && P.n_act < P.n) {                        // only the rows that pass the cut filter are packed and sorted
+            LAUNCH(blockcnt_scan_kernel, 1, 1024, 0, st, d_blockcnt, nblk);
+            LAUNCH(pack_compact_kernel, nblk, 256, 0, st, d_x, d_y, cut, P, d_blockcnt, k0, r0);
+            n_sort = P.n_act;
+        } else {
+            LAUNCH(pack_kernel<false>, cdiv(n, 1024), 256, 0, st, d_x, d_y, cut, P, k0, r0, (int*)nullptr, (int*)nullptr);
+        }
         stage_mark("pack", st);
         size_t sort_bytes = 0;
-        CU_TRY(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, k0, k1, r0, r1, (int)n, begin_bit, end_bit, st));
+        CU_TRY(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, k0, k1, r0, r1, n_sort, begin_bit, end_bit, st));
         void* d_sort;
         RET_IF(tmp.alloc((char**)&d_sort, sort_bytes));
-        CU_TRY(cub::DeviceRadixSort::SortPairs(d_sort, sort_bytes, k0, k1, r0, r1, (int)n, begin_bit, end_bit, st));
+        CU_TRY(cub::DeviceRadixSort::SortPairs(d_sort, sort_bytes, k0, k1, r0, r1, n_sort, begin_bit, end_bit, st));
         stage_mark("sort", st);
         LAUNCH(strip_table_search_kernel, cdiv(P.ns + 3, 256), 256, 0, st, ix->keys, P, ix->sstart);
     }

@@ -105,21 +105,30 @@ static void pass_release(cloops_pass* p, cudaStream_t st) {
 
 static int pass_run(cloops_pass* p, const int32_t* d_x, const int32_t* d_y, int64_t n, int32_t eps, int32_t minPts, int32_t cut,
                     int32_t variant, int32_t score, cudaStream_t st, int32_t* d_hist = nullptr, double* d_mom = nullptr) {
+    // every failure inside leaves through the common clean-up at the bottom (index, coverage model, join with the side stream)
+#define CU_BRK(expr)                                                                                                    \
+    {                                                                                                                   \
+        cudaError_t _e = (expr);                                                                                        \
+        if (_e != cudaSuccess) { rc = fail(CLOOPS_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); break; } \
+    }
     p->n = (int)n;
     if (n == 0) return 0;
     RET_IF(pool_init());
     cloops_coverage* cov = nullptr;
     Side* side = nullptr;
-    if (score) {                                   // fork: coverage sorts on the side stream
-        RET_IF(side_get(&side));
-        CU_TRY(cudaEventRecord(side->fork, st));
-        CU_TRY(cudaStreamWaitEvent(side->stream, side->fork, 0));
-        RET_IF(coverage_build(d_x, d_y, n, &cov, side->stream));
-        CU_TRY(cudaEventRecord(side->join, side->stream));
-    }
     int rc = 0;
     cloops_index* ix = nullptr;
+    bool forked = false;
     do {
+        if (score) {                               // fork: coverage sorts on the side stream
+            if ((rc = side_get(&side))) break;
+            CU_BRK(cudaEventRecord(side->fork, st));
+            CU_BRK(cudaStreamWaitEvent(side->stream, side->fork, 0));
+            forked = true;
+            rc = coverage_build(d_x, d_y, n, &cov, side->stream);
+            cudaEventRecord(side->join, side->stream);
+            if (rc) break;
+        }
         if (variant == CLOOPS_BLOCK) {             // no strip index: row order throughout
             p->n_members = (int)n;
             p->xs_owned = false;
@@ -161,16 +170,17 @@ static int pass_run(cloops_pass* p, const int32_t* d_x, const int32_t* d_y, int6
             cub::DeviceScan::ExclusiveSum(d_scan, bytes, flag, pos, k, st);
             cand_scatter_kernel<<<cdiv(k, 256), 256, 0, st>>>(p->kind, pos, p->bbox, k, p->cand, p->d_m);
             g_launches.fetch_add(1);
-            CU_TRY(cudaStreamWaitEvent(st, side->join, 0));      // join: coverage model ready
+            CU_BRK(cudaStreamWaitEvent(st, side->join, 0));      // join: coverage model ready
             if ((rc = range_counts_dev(cov, p->cand, k, p->d_m, p->counts, st))) break;
-            CU_TRY(cudaMemcpyAsync(&p->m, p->d_m, sizeof(int), cudaMemcpyDeviceToHost, st));
-            CU_TRY(cudaStreamSynchronize(st));
+            CU_BRK(cudaMemcpyAsync(&p->m, p->d_m, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CU_BRK(cudaStreamSynchronize(st));
             p->scored = 1;
             stage_mark("range_counts", st);
         }
     } while (0);
+#undef CU_BRK
     if (score) {
-        cudaStreamWaitEvent(st, side->join, 0);                   // never free the model while the side stream builds it
+        if (forked) cudaStreamWaitEvent(st, side->join, 0);       // never free the model while the side stream builds it
         cloops_coverage_release(cov, st);
         if (rc == 0) p->scored = 1;
     }

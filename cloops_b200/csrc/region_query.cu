@@ -350,21 +350,20 @@ __global__ void __launch_bounds__(CT_THREADS) count_kernel_tiled(const u64* __re
 
 
 // --------------------------------------------------------------------------------------------------
-// Region query, split form (round 2; the production kernel -- count_kernel_tiled above is kept for A/B runs,
-// CLOOPS_RQ=tiled).  Same tile, same W words and guards as above; what changes is how the work after the own strip
-// is organised, because in the tiled form every warp paid for the widest case of any of its lanes:
-//  * vmod is staged as 16-bit words (tiles with eps > 65536 take the global walk), the strip table as 16-bit slots:
-//    25 KB of shared memory per CTA with the two queues below.
-//  * phase 1 (own strip) as before for the templated caps; for caps >= 10 and exact counts the four nearest points on
-//    each side are register compares as well, then three saturation probes (the cap-1 nearest points to the left, to the
-//    right, and split around the point) settle the dense Hi-C diagonal in a handful of loads, and only points whose
-//    window reaches further scan on -- instead of two full uniform searches per point.
-//  * phase 2a: the unsaturated points (queue Q1) run the two uniform lower-bound searches and ONE load each to see
-//    whether the window in strip s-1 / s+1 holds anything at all (73 % do not at ChIA-PET density).  Non-empty
-//    windows are compacted into a second queue Q2 (point, slot of the first word, direction).
-//  * phase 2b: one thread per non-empty window walks it with the v test and adds to the point's count (shared atomic on
-//    the Q1 entry).  Only points that met a non-empty window rewrite their count (phase 3).
-// The uniform search is a straight ladder selected once per CTA by the tile's step count.
+// Region query, run form (round 2; the production kernel -- count_kernel_tiled above is kept for A/B runs,
+// CLOOPS_RQ=tiled).  Same tile, same W words and guards as above; what changes:
+//  * no queue and no second barrier: a thread keeps its FOUR CONSECUTIVE sorted points through both phases.  Consecutive
+//    points of a strip look at almost the same places of the adjacent strips, so only the thread's first unsaturated
+//    point pays the two uniform lower-bound searches; every following point continues from the previous point's bounds
+//    with a three-step search over the next seven words (a point that starts a new strip restarts at the adjacent
+//    strips' first words), and the full ladder is the fallback when that is not enough.  The tiled form paid two full
+//    searches per queued point plus the queue itself (scan, shared atomics, a barrier);
+//  * caps >= 10 and exact counts: the four nearest points on each side are register compares as for the small caps,
+//    then three saturation probes (the cap-1 nearest points to the left, to the right, or split around the point) settle
+//    the dense Hi-C diagonal in a handful of loads, and only windows that reach further are walked -- instead of two
+//    full uniform searches of the own strip per point;
+//  * vmod is staged as 16-bit words (tiles with eps > 65536 take the global walk) and the strip table as 16-bit slots:
+//    17.5 KB of shared memory per CTA; every count leaves the CTA once, as part of a 128-bit store.
 #define CQ_V16_BITS 16
 
 __device__ __forceinline__ u32 lds_u16(u32 a) {
@@ -373,46 +372,42 @@ __device__ __forceinline__ u32 lds_u16(u32 a) {
     return v;
 }
 
-#define CQ_STEP_CLAMPED(SB)                                   \
-    {                                                         \
-        const u32 na = min(pa + (SB), last_a);                \
-        if (lds_off<0>(na) < t) pa = na;                      \
-    }
-// as uniform_lower_bound, the halving steps unrolled into a ladder entered at the tile's step count
-__device__ __forceinline__ u32 ladder_lower_bound(u32 pa, u32 t, int nsteps, u32 last_a) {
-    switch (nsteps) {                                          // CTA-uniform
-        default:
-#pragma unroll 1
-            for (u32 sb = 2u << nsteps; sb > 4096u; sb >>= 1) CQ_STEP_CLAMPED(sb)
-        case 11: CQ_STEP_CLAMPED(4096u)
-        case 10: CQ_STEP_CLAMPED(2048u)
-        case 9: CQ_STEP_CLAMPED(1024u)
-        case 8: CQ_STEP_CLAMPED(512u)
-        case 7: CQ_STEP_CLAMPED(256u)
-        case 6: CQ_STEP_CLAMPED(128u)
-        case 5: CQ_STEP_CLAMPED(64u)
-        case 4: case 3: case 2: case 1: case 0: break;
-    }
-    if (lds_off<32>(pa) < t) pa += 32u;
+// first word >= t at or after the word following pa (W[pa] < t), looking at the next seven words only;
+// returns the address it reached (the caller checks the word there)
+__device__ __forceinline__ u32 near_lower_bound(u32 pa, u32 t) {
     if (lds_off<16>(pa) < t) pa += 16u;
     if (lds_off<8>(pa) < t) pa += 8u;
     if (lds_off<4>(pa) < t) pa += 4u;
     return pa + 4u;
 }
 
+// points of an adjacent strip from address ja on (W[ja] is the first word >= the window's lower end) that lie in the window
+// and pass the v test; stops at `room`.  w0 = W[ja], already loaded.
+template <bool NEXT>
+__device__ __forceinline__ int window_count(u32 ja, u32 w0, u32 w_a, u32 v_a, u32 thi, u32 vm, int room) {
+    int f = 0;
+    if (w0 <= thi) {
+        u32 va = v_a + ((ja - w_a) >> 1);
+        do {
+            const u32 v = lds_u16(va);
+            f += (NEXT ? v <= vm : v >= vm) ? 1 : 0;
+            ja += 4u;
+            va += 2u;
+        } while (f < room && lds_off<0>(ja) <= thi);
+    }
+    return f;
+}
+
 template <int CAPT>
-__global__ void __launch_bounds__(CT_THREADS) count_kernel_split(const u64* __restrict__ keys, const int* __restrict__ sstart,
-                                                                 const TileInfo* __restrict__ tiles, GridParams P, int cap_rt,
-                                                                 int* __restrict__ cnt, int vec_ok) {
+__global__ void __launch_bounds__(CT_THREADS) count_kernel_run(const u64* __restrict__ keys, const int* __restrict__ sstart,
+                                                               const TileInfo* __restrict__ tiles, GridParams P, int cap_rt,
+                                                               int* __restrict__ cnt, int vec_ok) {
     constexpr int RMAX = CT_RMAX;
     constexpr int NP = CAPT > 0 ? CAPT - 1 : 4;                          // register probes on each side
     constexpr int NV = NP > 4 ? 2 : 1;                                   // 128-bit words of context on each side
     __shared__ __align__(16) u32 Wg[RMAX + CT_G + 12 + 4];
     __shared__ __align__(16) unsigned short Vg[RMAX + CT_G + 12 + 4];
-    __shared__ __align__(16) u32 Q1[CT_TILE];                            // point | dirty << 10 | count << 12
-    __shared__ u32 Q2[2 * CT_TILE];                                      // Q1 index | slot << 10 | direction << 22
     __shared__ unsigned short S[CT_SMAX];
-    __shared__ int s_nq1, s_nq2;
     const int cap = CAPT > 0 ? CAPT : cap_rt;
     const int tid = threadIdx.x;
     const int t0 = blockIdx.x * CT_TILE;
@@ -426,7 +421,6 @@ __global__ void __launch_bounds__(CT_THREADS) count_kernel_split(const u64* __re
     const int be = P.be, bu = P.bu;
     const u32 eps = (u32)P.eps, one = 1u << bu, emask = P.emask;
     const int sl0 = CT_G - (r0 & ~3);             // slot of global index j = sl0 + j ; slot % 4 == j % 4
-    if (tid == 0) { s_nq1 = 0; s_nq2 = 0; }
     {
         const u32 base = (u32)((long long)(sA - 1) << bu);      // strip sA-1 -> relative strip 0 (mod 2^32)
         const ulonglong2* __restrict__ k2 = reinterpret_cast<const ulonglong2*>(keys);
@@ -460,153 +454,106 @@ __global__ void __launch_bounds__(CT_THREADS) count_kernel_split(const u64* __re
         if (tid >= 160 && tid < 160 + 12) Wg[sl0 + r1 + (tid - 160)] = 0xffffffffu;
     }
     __syncthreads();
+    const int i0 = t0 + 4 * tid;
+    if (i0 >= t1) return;
     const u32 w_a = (u32)__cvta_generic_to_shared(Wg);          // shared byte addresses
     const u32 v_a = (u32)__cvta_generic_to_shared(Vg);
-    const u32 q1_a = (u32)__cvta_generic_to_shared(Q1);
+    const u32 s_a = (u32)__cvta_generic_to_shared(S);
     const u32 first_a = w_a + 4u * (u32)(sl0 + r0 - CT_G);      // first left guard word
     const u32 last_a = w_a + 4u * (u32)(sl0 + r1);              // first right guard word
-    const int lane = tid & 31;
-    // ---- phase 1: own strip, four consecutive points per thread; saturated counts are final
-    const int i0 = t0 + 4 * tid;
+    // ---- phase 1: own strip, four consecutive points per thread
+    const int s0 = sl0 + i0;                                     // multiple of 4
+    unsigned nm = 0;                                             // bit k: point k is not saturated yet
+    int c[4];
+    u32 wq[4];
     {
-        unsigned nm = 0;                                                 // bit k: point k is not saturated yet
-        int c[4] = {0, 0, 0, 0};
-        if (i0 < t1) {
-            const int s0 = sl0 + i0;                                     // multiple of 4
-            u32 w[4 * (2 * NV + 1)];
+        u32 w[4 * (2 * NV + 1)];
 #pragma unroll
-            for (int v = 0; v < 2 * NV + 1; ++v) {
-                const uint4 x = *reinterpret_cast<const uint4*>(&Wg[s0 + 4 * (v - NV)]);
-                w[4 * v] = x.x; w[4 * v + 1] = x.y; w[4 * v + 2] = x.z; w[4 * v + 3] = x.w;
-            }
+        for (int v = 0; v < 2 * NV + 1; ++v) {
+            const uint4 x = *reinterpret_cast<const uint4*>(&Wg[s0 + 4 * (v - NV)]);
+            w[4 * v] = x.x; w[4 * v + 1] = x.y; w[4 * v + 2] = x.z; w[4 * v + 3] = x.w;
+        }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const u32 wp = w[4 * NV + k];
-                const u32 lo = wp - eps, hi = wp + eps;
-                int cc = 1;
-                if (CAPT > 0) {
+        for (int k = 0; k < 4; ++k) {
+            const u32 wp = w[4 * NV + k];
+            const u32 lo = wp - eps, hi = wp + eps;
+            wq[k] = wp;
+            int cc = 1;
+            if (CAPT > 0) {
 #pragma unroll
-                    for (int q = 1; q <= NP; ++q) {
-                        inc_ge(cc, w[4 * NV + k - q], lo);
-                        inc_le(cc, w[4 * NV + k + q], hi);
-                    }
-                } else {
-                    int cl = 0, cr = 0;
-#pragma unroll
-                    for (int q = 1; q <= NP; ++q) {
-                        inc_ge(cl, w[4 * NV + k - q], lo);
-                        inc_le(cr, w[4 * NV + k + q], hi);
-                    }
-                    cc = 1 + cl + cr;
-                    if ((cl == NP || cr == NP) && cc < cap && i0 + k < t1) {         // the window reaches past the register probes
-                        const int pa = (int)(w_a + 4u * (u32)(s0 + k));
-                        if (cap <= 0x10000) {                                        // saturation probes: cap-1 nearest on one side, or split
-                            const int far = 4 * (cap - 1), ha = 4 * ((cap - 1) >> 1), hb = far - ha;
-                            const bool sat = lds_off<0>((u32)max(pa - far, (int)first_a)) >= lo || lds_off<0>((u32)min(pa + far, (int)last_a)) <= hi ||
-                                             (lds_off<0>((u32)max(pa - ha, (int)first_a)) >= lo && lds_off<0>((u32)min(pa + hb, (int)last_a)) <= hi);
-                            if (sat) cc = cap;
-                        }
-                        if (cc < cap && cl == NP)
-                            for (u32 a = (u32)pa - 4u * (NP + 1); cc < cap && lds_off<0>(a) >= lo; a -= 4u) ++cc;
-                        if (cc < cap && cr == NP)
-                            for (u32 a = (u32)pa + 4u * (NP + 1); cc < cap && lds_off<0>(a) <= hi; a += 4u) ++cc;
-                    }
+                for (int q = 1; q <= NP; ++q) {
+                    inc_ge(cc, w[4 * NV + k - q], lo);
+                    inc_le(cc, w[4 * NV + k + q], hi);
                 }
-                c[k] = cc;
-                nm |= (cc < cap && i0 + k < t1) ? (1u << k) : 0u;
-            }
-            const int4 r = make_int4(min(c[0], cap), min(c[1], cap), min(c[2], cap), min(c[3], cap));
-            if (vec_ok && i0 + 3 < t1) {
-                *reinterpret_cast<int4*>(cnt + i0) = r;
             } else {
-                cnt[i0] = r.x;
-                if (i0 + 1 < t1) cnt[i0 + 1] = r.y;
-                if (i0 + 2 < t1) cnt[i0 + 2] = r.z;
-                if (i0 + 3 < t1) cnt[i0 + 3] = r.w;
-            }
-        }
-        // ---- queue of the points whose own strip did not saturate them (warp scan of the per-thread counts)
-        const int mine = __popc(nm);
-        int incl = mine;
+                int cl = 0, cr = 0;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int y = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += y;
+                for (int q = 1; q <= NP; ++q) {
+                    inc_ge(cl, w[4 * NV + k - q], lo);
+                    inc_le(cr, w[4 * NV + k + q], hi);
+                }
+                cc = 1 + cl + cr;
+                if ((cl == NP || cr == NP) && cc < cap && i0 + k < t1) {         // the window reaches past the register probes
+                    const int pa = (int)(w_a + 4u * (u32)(s0 + k));
+                    if (cap <= 0x10000) {                                        // saturation probes: cap-1 nearest on one side, or split
+                        const int far = 4 * (cap - 1), ha = 4 * ((cap - 1) >> 1), hb = far - ha;
+                        const bool sat = lds_off<0>((u32)max(pa - far, (int)first_a)) >= lo || lds_off<0>((u32)min(pa + far, (int)last_a)) <= hi ||
+                                         (lds_off<0>((u32)max(pa - ha, (int)first_a)) >= lo && lds_off<0>((u32)min(pa + hb, (int)last_a)) <= hi);
+                        if (sat) cc = cap;
+                    }
+                    if (cc < cap && cl == NP)
+                        for (u32 a = (u32)pa - 4u * (NP + 1); cc < cap && lds_off<0>(a) >= lo; a -= 4u) ++cc;
+                    if (cc < cap && cr == NP)
+                        for (u32 a = (u32)pa + 4u * (NP + 1); cc < cap && lds_off<0>(a) <= hi; a += 4u) ++cc;
+                }
+            }
+            c[k] = cc;
+            nm |= (cc < cap && i0 + k < t1) ? (1u << k) : 0u;
         }
-        const int tot = __shfl_sync(0xffffffffu, incl, 31);
-        if (tot) {                                                       // warp-uniform
-            int qb = 0;
-            if (lane == 0) qb = atomicAdd(&s_nq1, tot);
-            qb = __shfl_sync(0xffffffffu, qb, 0) + incl - mine;
-            u32 qa = q1_a + 4u * (u32)qb;                                // running store address
+    }
+    // ---- phase 2: strips s-1 and s+1 of the thread's unsaturated points, in index order
+    if (nm) {
+        u32 ja = 0, jb = 0, srel_prev = 0xffffffffu;
+        bool fresh = true;                                               // no bounds from a previous point yet
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const u32 e = (u32)(4 * tid + k) | ((u32)c[k] << 12);
-                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p st.shared.u32 [%0], %2;\n\t@p add.u32 %0, %0, 4;\n\t}"
-                             : "+r"(qa) : "r"(nm & (1u << k)), "r"(e) : "memory");
+        for (int k = 0; k < 4; ++k) {
+            if (!(nm & (1u << k))) continue;
+            const u32 wp = wq[k];
+            const u32 srel = wp >> bu;
+            const u32 tlo0 = wp - one - eps, tlo1 = wp + one - eps;
+            if (fresh) {
+                const u32 sr = s_a + 2u * srel;
+                ja = uniform_lower_bound(w_a + 4u * lds_u16(sr - 2u) - 4u, tlo0, nsteps, last_a);
+                jb = uniform_lower_bound(w_a + 4u * lds_u16(sr + 2u) - 4u, tlo1, nsteps, last_a);
+                fresh = false;
+            } else {
+                u32 pa = ja - 4u, pb = jb - 4u;                          // words known to lie below the new lower ends
+                if (srel != srel_prev) {                                 // first point of a new strip: restart at the adjacent strips' first words
+                    const u32 sr = s_a + 2u * srel;
+                    pa = w_a + 4u * lds_u16(sr - 2u) - 4u;
+                    pb = w_a + 4u * lds_u16(sr + 2u) - 4u;
+                }
+                ja = near_lower_bound(pa, tlo0);
+                jb = near_lower_bound(pb, tlo1);
+                if (lds_off<0>(ja) < tlo0) ja = uniform_lower_bound(ja, tlo0, nsteps, last_a);      // further than seven words: full ladder from here
+                if (lds_off<0>(jb) < tlo1) jb = uniform_lower_bound(jb, tlo1, nsteps, last_a);
             }
+            srel_prev = srel;
+            const u32 vm = lds_u16(v_a + 2u * (u32)(s0 + k));
+            int cc = c[k];
+            cc += window_count<false>(ja, lds_off<0>(ja), w_a, v_a, wp - one + eps, vm, cap - cc);
+            if (cc < cap) cc += window_count<true>(jb, lds_off<0>(jb), w_a, v_a, wp + one + eps, vm, cap - cc);
+            c[k] = cc;
         }
     }
-    __syncthreads();
-    // ---- phase 2a: both lower bounds of every queued point; non-empty windows go to Q2
-    const int nq1 = s_nq1;
-    if (nq1 == 0) return;                                                // CTA-uniform
-    {
-        const u32 s_a = (u32)__cvta_generic_to_shared(S);
-        const unsigned lt = (1u << lane) - 1u;
-#pragma unroll 1
-        for (int q0 = 0; q0 < nq1; q0 += CT_THREADS) {
-            const int q = q0 + tid;
-            const bool live = q < nq1;
-            const u32 e = live ? Q1[q] : 0u;
-            const u32 pa = w_a + 4u * (u32)(sl0 + t0 + (int)(e & 1023u));
-            const u32 wp = lds_off<0>(pa);
-            const u32 sr = s_a + 2u * (wp >> bu);                        // address of S[srel]
-            const u32 ja = ladder_lower_bound(w_a + 4u * lds_u16(sr - 2u) - 4u, wp - one - eps, nsteps, last_a);
-            const u32 jb = ladder_lower_bound(w_a + 4u * lds_u16(sr + 2u) - 4u, wp + one - eps, nsteps, last_a);
-            const bool hit0 = live && lds_off<0>(ja) <= wp - one + eps;
-            const bool hit1 = live && lds_off<0>(jb) <= wp + one + eps;
-            const unsigned b0 = __ballot_sync(0xffffffffu, hit0), b1 = __ballot_sync(0xffffffffu, hit1);
-            const int n0 = __popc(b0), tot = n0 + __popc(b1);
-            if (tot) {                                                   // warp-uniform
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&s_nq2, tot);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (hit0) Q2[base + __popc(b0 & lt)] = (u32)q | (((ja - w_a) >> 2) << 10);
-                if (hit1) Q2[base + n0 + __popc(b1 & lt)] = (u32)q | (((jb - w_a) >> 2) << 10) | (1u << 22);
-                if (hit0 || hit1) Q1[q] = e | 1024u;
-            }
-        }
-    }
-    __syncthreads();
-    // ---- phase 2b: one thread per non-empty window: v test on every point of the window, stopping once the point is saturated
-    const int nq2 = s_nq2;
-    if (nq2 == 0) return;                                                // CTA-uniform
-#pragma unroll 1
-    for (int x = tid; x < nq2; x += CT_THREADS) {
-        const u32 e2 = Q2[x];
-        const u32 qi = e2 & 1023u;
-        u32 i = (e2 >> 10) & 4095u;
-        const bool next = (e2 >> 22) != 0u;
-        const u32 e1 = *reinterpret_cast<volatile u32*>(&Q1[qi]);
-        const u32 slot = (u32)(sl0 + t0) + (e1 & 1023u);
-        const u32 wp = lds_off<0>(w_a + 4u * slot), vm = lds_u16(v_a + 2u * slot);
-        const u32 thi = next ? wp + one + eps : wp - one + eps;
-        const int room = cap - (int)(e1 >> 12);
-        int f = 0;
-        do {
-            const u32 v = lds_u16(v_a + 2u * i);
-            f += (next ? v <= vm : v >= vm) ? 1 : 0;
-            ++i;
-        } while (f < room && lds_off<0>(w_a + 4u * i) <= thi);
-        if (f) atomicAdd(&Q1[qi], (u32)f << 12);
-    }
-    __syncthreads();
-    // ---- phase 3: the points that met a non-empty window rewrite their count
-#pragma unroll 1
-    for (int q = tid; q < nq1; q += CT_THREADS) {
-        const u32 e = Q1[q];
-        if (e & 1024u) cnt[t0 + (int)(e & 1023u)] = min((int)(e >> 12), cap);
+    const int4 r = make_int4(min(c[0], cap), min(c[1], cap), min(c[2], cap), min(c[3], cap));
+    if (vec_ok && i0 + 3 < t1) {
+        *reinterpret_cast<int4*>(cnt + i0) = r;
+    } else {
+        cnt[i0] = r.x;
+        if (i0 + 1 < t1) cnt[i0 + 1] = r.y;
+        if (i0 + 2 < t1) cnt[i0 + 2] = r.z;
+        if (i0 + 3 < t1) cnt[i0 + 3] = r.w;
     }
 }
 
@@ -625,16 +572,16 @@ static int launch_count_tiled(const cloops_index* ix, int cap, int* out, cudaStr
     return 0;
 }
 
-static int launch_count_split(const cloops_index* ix, int cap, int* out, cudaStream_t st) {
+static int launch_count_run(const cloops_index* ix, int cap, int* out, cudaStream_t st) {
     const GridParams& P = ix->P;
     const int grid = cdiv(P.n_act, CT_TILE);
     const int vec_ok = (((uintptr_t)out) & 15) == 0 ? 1 : 0;
     const TileInfo* tiles = reinterpret_cast<const TileInfo*>(ix->tiles);
     switch (cap) {
-#define CQ_CASE(C) case C: LAUNCH((count_kernel_split<C>), grid, CT_THREADS, 0, st, ix->keys, ix->sstart, tiles, P, cap, out, vec_ok); break;
-        CQ_CASE(2) CQ_CASE(3) CQ_CASE(4) CQ_CASE(5) CQ_CASE(6) CQ_CASE(7) CQ_CASE(8) CQ_CASE(9)
-#undef CQ_CASE
-        default: LAUNCH((count_kernel_split<0>), grid, CT_THREADS, 0, st, ix->keys, ix->sstart, tiles, P, cap, out, vec_ok); break;
+#define CR_CASE(C) case C: LAUNCH((count_kernel_run<C>), grid, CT_THREADS, 0, st, ix->keys, ix->sstart, tiles, P, cap, out, vec_ok); break;
+        CR_CASE(2) CR_CASE(3) CR_CASE(4) CR_CASE(5) CR_CASE(6) CR_CASE(7) CR_CASE(8) CR_CASE(9)
+#undef CR_CASE
+        default: LAUNCH((count_kernel_run<0>), grid, CT_THREADS, 0, st, ix->keys, ix->sstart, tiles, P, cap, out, vec_ok); break;
     }
     return 0;
 }
@@ -655,7 +602,7 @@ int index_count(cloops_index* ix, int cap, int* d_counts_sorted, cudaStream_t st
     if (cap <= 0) cap = INT_MAX;
     static const bool use_tiled = getenv("CLOOPS_RQ") != nullptr && strcmp(getenv("CLOOPS_RQ"), "tiled") == 0;   // A/B knob
     if (use_tiled || P.be > CQ_V16_BITS) return launch_count_tiled<CT_RMAX>(ix, cap, d_counts_sorted, st);
-    return launch_count_split(ix, cap, d_counts_sorted, st);
+    return launch_count_run(ix, cap, d_counts_sorted, st);
 }
 
 }  // namespace cloops

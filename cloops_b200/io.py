@@ -130,8 +130,23 @@ def _cis_table(f, cs, cut):
             ok &= (b - a) >= cut
         cA[idx], cB[idx], keep[idx] = a, b, ok
         opp[idx] = cols[8].to_numpy(dtype=object)[idx] != cols[9].to_numpy(dtype=object)[idx]
-    for k in np.flatnonzero(slow).tolist():
-        t = [v for v in vals[k, :nfields[k]]]
+    raw = None
+    slow_idx = np.flatnonzero(slow).tolist()
+    if slow_idx:
+        # pandas pads short rows with "", so a row's true field count is only known up to its trailing empty fields: the
+        # slow path splits the raw text of those lines itself, exactly as the reference does (io.py:154)
+        with _open(f) as fh:
+            raw = fh.read().split("\n")
+        if len(raw) < n or (len(raw) > n and any(raw[n:])):       # line structure differs from the tokenizer's: per-line parser
+            raw = None
+    if slow_idx and raw is None:
+        rows = list(_cis_pets([f], cs, cut, _NullLog(), True))
+        return (np.array([r[0] for r in rows], dtype=object), np.array([r[1] for r in rows], dtype=np.int64),
+                np.array([r[2] for r in rows], dtype=np.int64), np.array([r[3] for r in rows], dtype=bool), getattr(_cis_pets, "total", 0))
+    for k in slow_idx:
+        t = raw[k].split("\t")
+        if ("*" in t and "-1" in t) or len(t) < 6:
+            continue
         try:
             pet = PET(t)
         except Exception:

@@ -28,9 +28,9 @@ def timed(ix, cap, out, iters=10):
     return ts[len(ts) // 2], ts[0]
 
 
-def run(name, X, Y, eps, caps):
+def run(name, X, Y, eps, caps, cut=0):
     dx, dy = device.to_device_i32(X), device.to_device_i32(Y)
-    ix = device.Index(dx, dy, eps)
+    ix = device.Index(dx, dy, eps, cut)
     n = ix.n_active
     for cap in caps:
         out = torch.full((n,), -7, dtype=torch.int32, device="cuda")
@@ -46,7 +46,15 @@ def run(name, X, Y, eps, caps):
 
 X, Y = synth.config2(10_000_000)
 run("config2-10M", X, Y, 1000, [5] if ncu_mode else [5, 0, 3, 9, 12])
+if ncu_mode:
+    X, Y = synth.genome_chrom(200_000_000, 4, 0)[1:]
+    run("config4-chr1", X, Y, 5000, [20], cut=11500)        # a later round of -m 3: the cut has removed the diagonal
+    run("config4-chr1", X, Y, 5000, [50])                   # round 1
 if not ncu_mode:
+    X, Y = synth.genome_chrom(200_000_000, 4, 0)[1:]
+    run("config4-chr1-cut11500", X, Y, 5000, [20], cut=11500)
+    run("config4-chr1-cut11500", X, Y, 10000, [50], cut=11500)
+    run("config4-chr1", X, Y, 5000, [50])
     run("config2-10M", X, Y, 250, [5])
     run("config2-10M", X, Y, 4000, [5])
     X, Y = synth.chromosome(16_000_000, 248_956_422, 20240 + 400, loop_frac=0.06, sigma=1500.0)
