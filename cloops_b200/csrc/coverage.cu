@@ -190,36 +190,56 @@ __global__ void __launch_bounds__(32 * RC_WARPS) range_count_ranked_kernel(const
             else O[(fam ? 13 : 3) + w - 1] = v;
         }
     }
-    // 3. joint table: every PET of in(A_i) against the B windows
+    // 3. joint table C_ij = #{p : in(A_i, p) and in(B_j, p)}: only PETs that touch BOTH families matter.  Walk the X ranges of
+    //    the hull(s) (a PET whose X lies outside every hull can only count through its Y, and then Y must lie in a window of
+    //    each family: second walk, over the Y range of the intersection of the two family hulls, usually empty).
     if (WIN > 0) {
-        const int fb0 = W.fb0, fb1 = W.fb1;
-        for (int i = 1; i < NW; ++i) {
-            const int* r = R + 4 * i;
-            const int2 ai = W.A[i];
-            int c[NW - 1];
-#pragma unroll
-            for (int j = 0; j < NW - 1; ++j) c[j] = 0;
-#pragma unroll 1
-            for (int view = 0; view < 2; ++view) {
-                const int lo = r[2 * view], hi = r[2 * view + 1];
-                const int* __restrict__ px = view ? ys_x : xs_x;
-                const int* __restrict__ py = view ? ys_y : xs_y;
-                for (int t = lo + lane; t < hi; t += 32) {
-                    const int x = __ldg(px + t), y = __ldg(py + t);
-                    if (view && (unsigned)(x - ai.x) <= (unsigned)ai.y) continue;      // already met through its X
-                    const bool xb = x >= fb0 && x <= fb1, yb = y >= fb0 && y <= fb1;
-                    if (!(xb || yb)) continue;
-#pragma unroll
-                    for (int j = 0; j < NW - 1; ++j) {
-                        const int2 bj = W.B[j + 1];
-                        c[j] += ((xb && (unsigned)(x - bj.x) <= (unsigned)bj.y) || (yb && (unsigned)(y - bj.x) <= (unsigned)bj.y)) ? 1 : 0;
-                    }
-                }
+        int* J = O + 23;
+        for (int t = lane; t < 100; t += 32) J[t] = 0;
+        __syncwarp();
+        const int fa0 = W.fa0, fa1 = W.fa1, fb0 = W.fb0, fb1 = W.fb1;
+        const int nh = W.nh;
+        const int i0 = max(fa0, fb0), i1 = min(fa1, fb1);                   // intersection of the family hulls
+        for (int pass = 0; pass <= nh; ++pass) {
+            int lo, hi;
+            const bool via_y = pass == nh;
+            if (!via_y) {
+                lo = lb_exact(xs_x, 0, n, W.h0[pass]);
+                hi = ub_exact(xs_x, lo, n, W.h1[pass]);
+            } else {
+                if (i0 > i1) break;
+                lo = lb_exact(ys_y, 0, n, i0);
+                hi = ub_exact(ys_y, lo, n, i1);
             }
-#pragma unroll
-            for (int j = 0; j < NW - 1; ++j) {
-                const int v = __reduce_add_sync(0xffffffffu, c[j]);
-                if (lane == 0) O[23 + 10 * (i - 1) + j] = v;
+            const int* __restrict__ px = via_y ? ys_x : xs_x;
+            const int* __restrict__ py = via_y ? ys_y : xs_y;
+            int t = lo + lane;
+            int xn = 0, yn = 0;
+            if (t < hi) { xn = __ldg(px + t); yn = __ldg(py + t); }
+            for (; t < hi; t += 32) {
+                const int x = xn, y = yn;
+                if (t + 32 < hi) { xn = __ldg(px + t + 32); yn = __ldg(py + t + 32); }
+                bool xa = x >= fa0 && x <= fa1, xb = x >= fb0 && x <= fb1;
+                if (via_y) {
+                    bool seen = false;                                       // X inside a hull: met in an earlier pass
+                    for (int g = 0; g < nh; ++g) seen |= (x >= W.h0[g] && x <= W.h1[g]);
+                    if (seen) continue;
+                    xa = xb = false;
+                }
+                const bool ya = y >= fa0 && y <= fa1, yb = y >= fb0 && y <= fb1;
+                if (!(xa || ya) || !(xb || yb)) continue;
+                unsigned ma = 0, mb = 0;
+                if (xa) ma |= window_mask(W.A, NW, x);
+                if (ya) ma |= window_mask(W.A, NW, y);
+                ma >>= 1;                                                    // the shifted windows only
+                if (ma == 0) continue;
+                if (xb) mb |= window_mask(W.B, NW, x);
+                if (yb) mb |= window_mask(W.B, NW, y);
+                mb >>= 1;
+                for (unsigned r = ma; r; r &= r - 1) {
+                    const int i = __ffs(r) - 1;
+                    for (unsigned q = mb; q; q &= q - 1) atomicAdd(&J[10 * i + (__ffs(q) - 1)], 1);
+                }
             }
         }
     }
@@ -361,15 +381,14 @@ int coverage_build(const int32_t* d_x, const int32_t* d_y, int64_t n, cloops_cov
 }
 
 // d_ncand != NULL: the candidate count is read on the device (no host round trip); ncand is then an upper bound
-// Which form counts the 123 integers (WIN = 5): measured on the config-4 step (437 k scored candidates, anchors ~19 kb wide,
-// overlapping A / B hulls) the ranked form's joint table costs as much as the legacy walk (322 vs 260 ms per step), so the
-// legacy form stays the default there; for (ra, rb, rab) alone (WIN = 0, cloops_region_pets) the ranked form is 6.7 x faster
-// (60.5 -> 9 ms per step) and is the default.  CLOOPS_RC=ranked / legacy forces one form for both.
-static int rc_mode() {
-    static const int v = getenv("CLOOPS_RC") == nullptr ? 0 : (strcmp(getenv("CLOOPS_RC"), "legacy") == 0 ? 1 : (strcmp(getenv("CLOOPS_RC"), "ranked") == 0 ? 2 : 0));
+// CLOOPS_RC=legacy selects the round-1 walk for A/B runs.  Measured on the config-4 step (437 k scored candidates of 1.23 M,
+// anchors ~19 kb wide, mostly overlapping A / B hulls): 123 integers 260 -> 148 ms per step, (ra, rb, rab) of all candidates
+// 60.5 -> 8.9 ms per step (profiles/r02_bench_c4_ranked.json / _legacy.json).
+static bool rc_legacy(int win = 5) {
+    static const bool v = getenv("CLOOPS_RC") != nullptr && strcmp(getenv("CLOOPS_RC"), "legacy") == 0;
+    (void)win;
     return v;
 }
-static bool rc_legacy(int win = 5) { return rc_mode() == 1 || (rc_mode() == 0 && win > 0); }
 
 int range_counts_dev(const cloops_coverage* cov, const int32_t* d_cand, int64_t ncand, const int* d_ncand, int32_t* d_out,
                      cudaStream_t st) {

@@ -6,8 +6,6 @@
 // restricted to u in [u-eps, u+eps]); inside the own strip |dv| <= eps-1 holds by construction, in strip s-1 (s+1) the
 // remaining test is vmod_q >= vmod_p (vmod_q <= vmod_p).
 #include <limits.h>
-#include <stdlib.h>
-#include <string.h>
 
 #include <type_traits>
 
@@ -348,215 +346,6 @@ __global__ void __launch_bounds__(CT_THREADS) count_kernel_tiled(const u64* __re
     }
 }
 
-
-// --------------------------------------------------------------------------------------------------
-// Region query, run form (round 2; the production kernel -- count_kernel_tiled above is kept for A/B runs,
-// CLOOPS_RQ=tiled).  Same tile, same W words and guards as above; what changes:
-//  * no queue and no second barrier: a thread keeps its FOUR CONSECUTIVE sorted points through both phases.  Consecutive
-//    points of a strip look at almost the same places of the adjacent strips, so only the thread's first unsaturated
-//    point pays the two uniform lower-bound searches; every following point continues from the previous point's bounds
-//    with a three-step search over the next seven words (a point that starts a new strip restarts at the adjacent
-//    strips' first words), and the full ladder is the fallback when that is not enough.  The tiled form paid two full
-//    searches per queued point plus the queue itself (scan, shared atomics, a barrier);
-//  * caps >= 10 and exact counts: the four nearest points on each side are register compares as for the small caps,
-//    then three saturation probes (the cap-1 nearest points to the left, to the right, or split around the point) settle
-//    the dense Hi-C diagonal in a handful of loads, and only windows that reach further are walked -- instead of two
-//    full uniform searches of the own strip per point;
-//  * vmod is staged as 16-bit words (tiles with eps > 65536 take the global walk) and the strip table as 16-bit slots:
-//    17.5 KB of shared memory per CTA; every count leaves the CTA once, as part of a 128-bit store.
-#define CQ_V16_BITS 16
-
-__device__ __forceinline__ u32 lds_u16(u32 a) {
-    unsigned short v;
-    asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
-    return v;
-}
-
-// first word >= t at or after the word following pa (W[pa] < t), looking at the next seven words only;
-// returns the address it reached (the caller checks the word there)
-__device__ __forceinline__ u32 near_lower_bound(u32 pa, u32 t) {
-    if (lds_off<16>(pa) < t) pa += 16u;
-    if (lds_off<8>(pa) < t) pa += 8u;
-    if (lds_off<4>(pa) < t) pa += 4u;
-    return pa + 4u;
-}
-
-// points of an adjacent strip from address ja on (W[ja] is the first word >= the window's lower end) that lie in the window
-// and pass the v test; stops at `room`.  w0 = W[ja], already loaded.
-template <bool NEXT>
-__device__ __forceinline__ int window_count(u32 ja, u32 w0, u32 w_a, u32 v_a, u32 thi, u32 vm, int room) {
-    int f = 0;
-    if (w0 <= thi) {
-        u32 va = v_a + ((ja - w_a) >> 1);
-        do {
-            const u32 v = lds_u16(va);
-            f += (NEXT ? v <= vm : v >= vm) ? 1 : 0;
-            ja += 4u;
-            va += 2u;
-        } while (f < room && lds_off<0>(ja) <= thi);
-    }
-    return f;
-}
-
-template <int CAPT>
-__global__ void __launch_bounds__(CT_THREADS) count_kernel_run(const u64* __restrict__ keys, const int* __restrict__ sstart,
-                                                               const TileInfo* __restrict__ tiles, GridParams P, int cap_rt,
-                                                               int* __restrict__ cnt, int vec_ok) {
-    constexpr int RMAX = CT_RMAX;
-    constexpr int NP = CAPT > 0 ? CAPT - 1 : 4;                          // register probes on each side
-    constexpr int NV = NP > 4 ? 2 : 1;                                   // 128-bit words of context on each side
-    __shared__ __align__(16) u32 Wg[RMAX + CT_G + 12 + 4];
-    __shared__ __align__(16) unsigned short Vg[RMAX + CT_G + 12 + 4];
-    __shared__ unsigned short S[CT_SMAX];
-    const int cap = CAPT > 0 ? CAPT : cap_rt;
-    const int tid = threadIdx.x;
-    const int t0 = blockIdx.x * CT_TILE;
-    const int t1 = min(t0 + CT_TILE, P.n_act);
-    const int4 ti = __ldg(reinterpret_cast<const int4*>(tiles) + blockIdx.x);
-    const int sA = ti.x, r0 = ti.y, r1 = ti.z, nse = ti.w & 0xffff, nsteps = ti.w >> 16;
-    if (nse == 0) {                               // CTA-uniform: the staged range does not fit
-        for (int i = t0 + tid; i < t1; i += CT_THREADS) cnt[i] = count_point_global(keys, sstart, P, cap, i);
-        return;
-    }
-    const int be = P.be, bu = P.bu;
-    const u32 eps = (u32)P.eps, one = 1u << bu, emask = P.emask;
-    const int sl0 = CT_G - (r0 & ~3);             // slot of global index j = sl0 + j ; slot % 4 == j % 4
-    {
-        const u32 base = (u32)((long long)(sA - 1) << bu);      // strip sA-1 -> relative strip 0 (mod 2^32)
-        const ulonglong2* __restrict__ k2 = reinterpret_cast<const ulonglong2*>(keys);
-        const int p_hi = r1 >> 1;
-        const int j2 = ((r0 + 1) >> 1) + tid;                   // whole key pairs inside [r0, r1)
-        auto put = [&](int j, const ulonglong2& kk) {
-            const int sl = sl0 + 2 * j;                         // even
-            *reinterpret_cast<uint2*>(&Wg[sl]) = make_uint2((u32)(kk.x >> be) - base, (u32)(kk.y >> be) - base);
-            *reinterpret_cast<u32*>(&Vg[sl]) = ((u32)kk.x & emask) | (((u32)kk.y & emask) << 16);
-        };
-        ulonglong2 kk[3];                                       // all loads of the common case in flight at once
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-            if (j2 + k * CT_THREADS < p_hi) kk[k] = __ldg(k2 + j2 + k * CT_THREADS);
-#pragma unroll 1
-        for (int k = tid; k < nse; k += CT_THREADS) S[k] = (unsigned short)(__ldg(sstart + sA + k) + sl0);   // strip offsets as slots
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-            if (j2 + k * CT_THREADS < p_hi) put(j2 + k * CT_THREADS, kk[k]);
-#pragma unroll 1
-        for (int j = j2 + 3 * CT_THREADS; j < p_hi; j += CT_THREADS) put(j, __ldg(k2 + j));
-        if (tid >= 64 && tid < 66) {                            // the unpaired first / last point
-            const int j = tid == 64 ? r0 : r1 - 1;
-            if (j & 1 ? tid == 64 : tid == 65) {
-                const u64 k = __ldg(keys + j);
-                Wg[sl0 + j] = (u32)(k >> be) - base;
-                Vg[sl0 + j] = (unsigned short)((u32)k & emask);
-            }
-        }
-        if (tid >= 128 && tid < 128 + CT_G) Wg[sl0 + r0 - 1 - (tid - 128)] = 0u;
-        if (tid >= 160 && tid < 160 + 12) Wg[sl0 + r1 + (tid - 160)] = 0xffffffffu;
-    }
-    __syncthreads();
-    const int i0 = t0 + 4 * tid;
-    if (i0 >= t1) return;
-    const u32 w_a = (u32)__cvta_generic_to_shared(Wg);          // shared byte addresses
-    const u32 v_a = (u32)__cvta_generic_to_shared(Vg);
-    const u32 s_a = (u32)__cvta_generic_to_shared(S);
-    const u32 first_a = w_a + 4u * (u32)(sl0 + r0 - CT_G);      // first left guard word
-    const u32 last_a = w_a + 4u * (u32)(sl0 + r1);              // first right guard word
-    // ---- phase 1: own strip, four consecutive points per thread
-    const int s0 = sl0 + i0;                                     // multiple of 4
-    unsigned nm = 0;                                             // bit k: point k is not saturated yet
-    int c[4];
-    u32 wq[4];
-    {
-        u32 w[4 * (2 * NV + 1)];
-#pragma unroll
-        for (int v = 0; v < 2 * NV + 1; ++v) {
-            const uint4 x = *reinterpret_cast<const uint4*>(&Wg[s0 + 4 * (v - NV)]);
-            w[4 * v] = x.x; w[4 * v + 1] = x.y; w[4 * v + 2] = x.z; w[4 * v + 3] = x.w;
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const u32 wp = w[4 * NV + k];
-            const u32 lo = wp - eps, hi = wp + eps;
-            wq[k] = wp;
-            int cc = 1;
-            if (CAPT > 0) {
-#pragma unroll
-                for (int q = 1; q <= NP; ++q) {
-                    inc_ge(cc, w[4 * NV + k - q], lo);
-                    inc_le(cc, w[4 * NV + k + q], hi);
-                }
-            } else {
-                int cl = 0, cr = 0;
-#pragma unroll
-                for (int q = 1; q <= NP; ++q) {
-                    inc_ge(cl, w[4 * NV + k - q], lo);
-                    inc_le(cr, w[4 * NV + k + q], hi);
-                }
-                cc = 1 + cl + cr;
-                if ((cl == NP || cr == NP) && cc < cap && i0 + k < t1) {         // the window reaches past the register probes
-                    const int pa = (int)(w_a + 4u * (u32)(s0 + k));
-                    if (cap <= 0x10000) {                                        // saturation probes: cap-1 nearest on one side, or split
-                        const int far = 4 * (cap - 1), ha = 4 * ((cap - 1) >> 1), hb = far - ha;
-                        const bool sat = lds_off<0>((u32)max(pa - far, (int)first_a)) >= lo || lds_off<0>((u32)min(pa + far, (int)last_a)) <= hi ||
-                                         (lds_off<0>((u32)max(pa - ha, (int)first_a)) >= lo && lds_off<0>((u32)min(pa + hb, (int)last_a)) <= hi);
-                        if (sat) cc = cap;
-                    }
-                    if (cc < cap && cl == NP)
-                        for (u32 a = (u32)pa - 4u * (NP + 1); cc < cap && lds_off<0>(a) >= lo; a -= 4u) ++cc;
-                    if (cc < cap && cr == NP)
-                        for (u32 a = (u32)pa + 4u * (NP + 1); cc < cap && lds_off<0>(a) <= hi; a += 4u) ++cc;
-                }
-            }
-            c[k] = cc;
-            nm |= (cc < cap && i0 + k < t1) ? (1u << k) : 0u;
-        }
-    }
-    // ---- phase 2: strips s-1 and s+1 of the thread's unsaturated points, in index order
-    if (nm) {
-        u32 ja = 0, jb = 0, srel_prev = 0xffffffffu;
-        bool fresh = true;                                               // no bounds from a previous point yet
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (!(nm & (1u << k))) continue;
-            const u32 wp = wq[k];
-            const u32 srel = wp >> bu;
-            const u32 tlo0 = wp - one - eps, tlo1 = wp + one - eps;
-            if (fresh) {
-                const u32 sr = s_a + 2u * srel;
-                ja = uniform_lower_bound(w_a + 4u * lds_u16(sr - 2u) - 4u, tlo0, nsteps, last_a);
-                jb = uniform_lower_bound(w_a + 4u * lds_u16(sr + 2u) - 4u, tlo1, nsteps, last_a);
-                fresh = false;
-            } else {
-                u32 pa = ja - 4u, pb = jb - 4u;                          // words known to lie below the new lower ends
-                if (srel != srel_prev) {                                 // first point of a new strip: restart at the adjacent strips' first words
-                    const u32 sr = s_a + 2u * srel;
-                    pa = w_a + 4u * lds_u16(sr - 2u) - 4u;
-                    pb = w_a + 4u * lds_u16(sr + 2u) - 4u;
-                }
-                ja = near_lower_bound(pa, tlo0);
-                jb = near_lower_bound(pb, tlo1);
-                if (lds_off<0>(ja) < tlo0) ja = uniform_lower_bound(ja, tlo0, nsteps, last_a);      // further than seven words: full ladder from here
-                if (lds_off<0>(jb) < tlo1) jb = uniform_lower_bound(jb, tlo1, nsteps, last_a);
-            }
-            srel_prev = srel;
-            const u32 vm = lds_u16(v_a + 2u * (u32)(s0 + k));
-            int cc = c[k];
-            cc += window_count<false>(ja, lds_off<0>(ja), w_a, v_a, wp - one + eps, vm, cap - cc);
-            if (cc < cap) cc += window_count<true>(jb, lds_off<0>(jb), w_a, v_a, wp + one + eps, vm, cap - cc);
-            c[k] = cc;
-        }
-    }
-    const int4 r = make_int4(min(c[0], cap), min(c[1], cap), min(c[2], cap), min(c[3], cap));
-    if (vec_ok && i0 + 3 < t1) {
-        *reinterpret_cast<int4*>(cnt + i0) = r;
-    } else {
-        cnt[i0] = r.x;
-        if (i0 + 1 < t1) cnt[i0 + 1] = r.y;
-        if (i0 + 2 < t1) cnt[i0 + 2] = r.z;
-        if (i0 + 3 < t1) cnt[i0 + 3] = r.w;
-    }
-}
-
 template <int RMAX>
 static int launch_count_tiled(const cloops_index* ix, int cap, int* out, cudaStream_t st) {
     const GridParams& P = ix->P;
@@ -572,19 +361,6 @@ static int launch_count_tiled(const cloops_index* ix, int cap, int* out, cudaStr
     return 0;
 }
 
-static int launch_count_run(const cloops_index* ix, int cap, int* out, cudaStream_t st) {
-    const GridParams& P = ix->P;
-    const int grid = cdiv(P.n_act, CT_TILE);
-    const int vec_ok = (((uintptr_t)out) & 15) == 0 ? 1 : 0;
-    const TileInfo* tiles = reinterpret_cast<const TileInfo*>(ix->tiles);
-    switch (cap) {
-#define CR_CASE(C) case C: LAUNCH((count_kernel_run<C>), grid, CT_THREADS, 0, st, ix->keys, ix->sstart, tiles, P, cap, out, vec_ok); break;
-        CR_CASE(2) CR_CASE(3) CR_CASE(4) CR_CASE(5) CR_CASE(6) CR_CASE(7) CR_CASE(8) CR_CASE(9)
-#undef CR_CASE
-        default: LAUNCH((count_kernel_run<0>), grid, CT_THREADS, 0, st, ix->keys, ix->sstart, tiles, P, cap, out, vec_ok); break;
-    }
-    return 0;
-}
 
 // per-tile headers of an index (called once by index_build)
 int index_tiles(cloops_index* ix, cudaStream_t st) {
@@ -600,9 +376,7 @@ int index_count(cloops_index* ix, int cap, int* d_counts_sorted, cudaStream_t st
     const GridParams& P = ix->P;
     if (P.n_act == 0) return 0;
     if (cap <= 0) cap = INT_MAX;
-    static const bool use_tiled = getenv("CLOOPS_RQ") != nullptr && strcmp(getenv("CLOOPS_RQ"), "tiled") == 0;   // A/B knob
-    if (use_tiled || P.be > CQ_V16_BITS) return launch_count_tiled<CT_RMAX>(ix, cap, d_counts_sorted, st);
-    return launch_count_run(ix, cap, d_counts_sorted, st);
+    return launch_count_tiled<CT_RMAX>(ix, cap, d_counts_sorted, st);
 }
 
 }  // namespace cloops
