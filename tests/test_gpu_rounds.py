@@ -1,0 +1,81 @@
+"""The multi-round engine on resident chromosomes (pipe.call_loops: what bench.py times for configs 3 / 4) against an
+oracle pipeline built from the C oracle and the reference's numpy cut-off estimate: per round the cut filter, cDBSCAN2
+labels, candidate records, pooled dis / dss -> estIntSelCutFrag (cLoops/pipe.py:247-281, ests.py:36-61), then combineTwice
+and filterClusterByDis.  The device-side statistics (histogram + log2 moments, one reduction per round) must give the same
+integer cut-offs, and the candidates that reach scoring must be the same boxes in the same order."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def oracle_rounds(chroms, eps_list, mp_list):
+    from cloops_b200 import ests
+    from oracle import coracle
+    cut, cuts = 0, [0]
+    recs = {name: [] for name, _, _ in chroms}
+    trace = []
+    for ep in eps_list:
+        for m in mp_list:
+            dis, dss, contributed = [], [], 0
+            for name, X, Y in chroms:
+                d = Y - X
+                act = d >= cut if cut > 0 else np.ones(len(d), bool)
+                lab = np.full(len(X), -1, np.int32)
+                if act.any():
+                    lab[act] = coracle.dbscan(X[act], Y[act], ep, m, coracle.V2)
+                bbox, size, kind = coracle.cluster_records(X, Y, lab)
+                inter = bbox[kind == 1]
+                if len(inter) == 0:                                 # pipe.py:121-122
+                    continue
+                contributed += 1
+                recs[name].append(inter)
+                dis.append(d[np.isin(lab, np.flatnonzero(kind == 1))])
+                if cut > 0:
+                    dss.append(d[~act])
+                if (kind == 2).any():
+                    dss.append(d[np.isin(lab, np.flatnonzero(kind == 2))])
+            dis = np.concatenate(dis) if dis else np.zeros(0)
+            dss = np.concatenate(dss) if dss else np.zeros(0)
+            if contributed and len(dis) and len(dss):
+                cut = ests.estIntSelCutFrag(dis, dss)[0]
+                cuts.append(cut)
+            trace.append((ep, m, cut, len(dis), len(dss)))
+    final = min(c for c in cuts if c > 0)
+    out = {}
+    for name, rounds in recs.items():
+        if not rounds:
+            continue
+        seen, keep = set(), []
+        for r in rounds:                                            # combineTwice, pipe.py:155-174
+            rows = [tuple(x) for x in r.tolist()]
+            keep += [x for x in rows if x not in seen]
+            seen |= set(rows)
+        r = np.array(keep, np.int64).reshape(-1, 4)
+        out[name] = r[(r[:, 2] + r[:, 3]) // 2 - (r[:, 0] + r[:, 1]) // 2 >= final]     # filterClusterByDis, pipe.py:130-143
+    return out, final, trace
+
+
+@pytest.mark.parametrize("eps_list,mp_list,dens", [([2000, 4000], [12, 6], 0.4), ([5000, 7500], [30, 20], 1.0)])
+def test_rounds_match_oracle_pipeline(eps_list, mp_list, dens, monkeypatch):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from cloops_b200 import pipe, synth
+    chroms = []
+    for k, (n, L) in enumerate(((300_000, 5_000_000), (180_000, 3_000_000), (90_000, 2_000_000))):
+        X, Y = synth.chromosome(int(n * dens), L, seed=900 + k, loop_frac=0.1, sigma=800.0)
+        chroms.append(("chr%d" % (k + 1), X.astype(np.int64), Y.astype(np.int64)))
+    want, final, trace = oracle_rounds(chroms, eps_list, mp_list)
+    pipe._Resident.clear()
+    cfs = [pipe._Resident.register(name, X, Y) for name, X, Y in chroms]
+    seen = []
+    orig = pipe._round
+    monkeypatch.setattr(pipe, "_round", lambda fs, e, m, c, w=None: (lambda r: (seen.append((e, m, r[4], r[2], r[3])), r)[1])(orig(fs, e, m, c, w)))
+    run = pipe.call_loops(cfs, eps_list, mp_list, hic=1, tail=False)
+    pipe._Resident.clear()
+    assert [(e, m, c, nd, ns) for e, m, c, nd, ns in seen] == [(e, m, c, nd, ns) for e, m, c, nd, ns in trace]
+    assert run["cut"] == final
+    assert sorted(k[0] for k in run["dataI"]) == sorted(want)
+    for key, v in run["dataI"].items():
+        assert np.array_equal(np.asarray(v["records"], np.int64), want[key[0]]), key
