@@ -130,6 +130,7 @@ def quiet_logs():
     lg = logging.getLogger("cloops_bench")
     lg.handlers, lg.propagate = [logging.NullHandler()], False
     pipe.logger = lg
+    pipe.cModel.QUIET = True
     sys.stderr = open(os.devnull, "w") if os.environ.get("CLOOPS_BENCH_VERBOSE") is None else sys.stderr
 
 

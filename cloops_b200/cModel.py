@@ -61,6 +61,13 @@ class CoverageModel:
 
 #: set by pipe.py: f -> the chromosome object already resident in HBM (key, X, Y, dx, dy), or None
 RESIDENT = None
+#: the reference reports progress with print() (cModel.py:268-270); bench.py silences it so that its stdout is one JSON line
+QUIET = False
+
+
+def _say(msg):
+    if not QUIET:
+        print(msg)
 
 
 def getGenomeCoverage(f, cut=0):
@@ -273,11 +280,11 @@ def countCandidates(f, records, minPts, discut):
     """The GPU half of getIntSig (cModel.py:262-295): coverage model, (ra, rb, rab) of every candidate, the rab / distance
     filters (:284-291) and the 123 permuted-background integers of the survivors.
     -> None (no model: fewer than 2 PETs) or dict(N, names, cand, keep, dist, counts)."""
-    print("Starting estimate significance for %s candidate interactions in %s" % (len(records), f))
+    _say("Starting estimate significance for %s candidate interactions in %s" % (len(records), f))
     model, N = getGenomeCoverage(f, discut)
-    print("Genomic coverage model built from %s" % f)
+    _say("Genomic coverage model built from %s" % f)
     if N == 0:
-        print("No cis-PETs parsed as requiring distance cutoff >%s from %s" % (discut, f))
+        _say("No cis-PETs parsed as requiring distance cutoff >%s from %s" % (discut, f))
         return None
     if isinstance(records, np.ndarray):                  # pipe(): int array [K,4] = minX, maxX, minY, maxY
         cand = records.astype(np.int64).reshape(-1, 4)

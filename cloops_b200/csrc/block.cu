@@ -15,6 +15,7 @@
 #include <cub/cub.cuh>
 
 #include "common.cuh"
+#include "scan.cuh"
 
 namespace cloops {
 
@@ -313,11 +314,9 @@ int block_dbscan(const int32_t* d_x, const int32_t* d_y, int64_t n, int32_t eps,
     RET_IF(tmp.alloc(&counters, 8));
     CU_TRY(cudaMemsetAsync(counters, 0, 8 * sizeof(int), st));
     LAUNCH(bhead_kernel, cdiv(na, 256), 256, 0, st, k1, na, head);
-    bytes = 0;
-    CU_TRY(cub::DeviceScan::InclusiveSum(nullptr, bytes, head, cellidx, na, st));
-    void* d_tmp2;
-    RET_IF(tmp.alloc((char**)&d_tmp2, bytes));
-    CU_TRY(cub::DeviceScan::InclusiveSum(d_tmp2, bytes, head, cellidx, na, st));
+    int* d_scan;
+    RET_IF(tmp.alloc(&d_scan, scan_tmp_ints((long long)n + 1)));
+    RET_IF((device_scan<SCAN_ADD, true, false>(head, cellidx, na, d_scan, st)));
     int ncell = 0;
     CU_TRY(cudaMemcpyAsync(&ncell, cellidx + na - 1, sizeof(int), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
@@ -358,11 +357,7 @@ int block_dbscan(const int32_t* d_x, const int32_t* d_y, int64_t n, int32_t eps,
     LAUNCH(bcompress_kernel, gc, 256, 0, st, C, ncell, minPts, counters);
     if (ne > 0) LAUNCH(bborder_kernel, cdiv(ne, 256), 256, 0, st, C, ea, eb, ne, minPts, flags);
     LAUNCH(bflags_kernel, gc, 256, 0, st, C, ncell, minPts, flags);
-    bytes = 0;
-    CU_TRY(cub::DeviceScan::ExclusiveSum(nullptr, bytes, flags, ids, (int)n + 1, st));
-    void* d_tmp3;
-    RET_IF(tmp.alloc((char**)&d_tmp3, bytes));
-    CU_TRY(cub::DeviceScan::ExclusiveSum(d_tmp3, bytes, flags, ids, (int)n + 1, st));
+    RET_IF((device_scan<SCAN_ADD, false, false>(flags, ids, (long long)n + 1, d_scan, st)));
     LAUNCH(blabel_kernel, cdiv(na, 256), 256, 0, st, C, cellidx, r1, na, minPts, ids, d_labels, counters);
     stage_mark("labels", st);
     if (h_info) {

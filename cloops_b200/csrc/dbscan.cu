@@ -14,10 +14,8 @@
 #include <limits.h>
 #include <stdlib.h>
 
-#include <cub/cub.cuh>
-#include <thrust/iterator/reverse_iterator.h>
-
 #include "index.cuh"
+#include "scan.cuh"
 
 namespace cloops {
 
@@ -44,7 +42,27 @@ struct Work {
     int* counters;   // [8]: 0 n_und, 1 n_con, 2 remaining, 3 n_dead, 4 n_comp
     int* slots_core; // [CTR_SLOTS*CTR_STRIDE] spread partial sums of n_core
     int* slots_lab;  // same for n_labelled
+    u32* corebits;   // [CB_WORDS] hashed bitmap of the rotated cells that hold a core point (border pruning)
 };
+
+// A non-core point can only be a border point if one of the 3 x 3 rotated floor cells around it holds a core point
+// (|du|, |dv| <= eps).  Core points mark their cell in a hashed bitmap (2^26 bits = 8 MB, L2-resident); the border kernels
+// probe the nine cells first and skip the neighbour walk when none is marked.  A hash collision can only cause a needless
+// walk, never a missed one.  At Hi-C depth (minPts 20-50) core points are confined to the clusters, so most PETs skip.
+#define CB_BITS 26
+#define CB_WORDS (1u << (CB_BITS - 5))
+__device__ __forceinline__ u32 cb_hash(u32 strip, u32 cu) { return (strip * 0x9E3779B1u + cu * 0x85EBCA77u) >> (32 - CB_BITS); }
+__device__ __forceinline__ bool cb_any_core_near(const u32* __restrict__ bits, u32 strip, u32 cu) {
+    bool any = false;
+#pragma unroll
+    for (int ds = -1; ds <= 1; ++ds)
+#pragma unroll
+        for (int dc = -1; dc <= 1; ++dc) {
+            const u32 h = cb_hash(strip + (u32)ds, cu + (u32)dc);
+            any |= (__ldg(bits + (h >> 5)) >> (h & 31u)) & 1u;
+        }
+    return any;
+}
 
 // Informational totals (n_core, n_labelled): one atomic per CTA, spread over CTR_SLOTS addresses 128 B
 // apart -- the L2 atomic unit serialises same-address atomics (~0.5 us per thousand), which made a
@@ -89,6 +107,10 @@ __global__ void __launch_bounds__(256) flag_kernel(u64* __restrict__ keys, GridP
         W.ncore[i] = 0;
         W.size[i] = 0;
         W.status[i] = ST_NONE;
+        if (core) {
+            const u32 h = cb_hash((u32)(k >> P.sshift), ((u32)(k >> P.be) & P.umask) / (u32)P.eps);
+            atomicOr(&W.corebits[h >> 5], 1u << (h & 31u));
+        }
         if (want_cells) {
             // rotated floor cell = (strip, floor(u'/eps)) (cDBSCAN2.py:69-70); head = first sorted point of the cell
             bool head = true;
@@ -286,7 +308,11 @@ __global__ void __launch_bounds__(256) v1_border_kernel(const u64* __restrict__ 
     __shared__ int s_n;
     {
         const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
-        const bool todo = i0 < P.n_act && !(keys[i0] >> 63);
+        bool todo = i0 < P.n_act && !(keys[i0] >> 63);
+        if (todo) {                                         // no core point in the 3 x 3 cells around it: cannot be a border point
+            const u64 k0 = keys[i0];
+            todo = cb_any_core_near(W.corebits, (u32)(k0 >> P.sshift), ((u32)(k0 >> P.be) & P.umask) / (u32)P.eps);
+        }
         if ((int)threadIdx.x >= cta_compact(todo, q, &s_n)) return;
     }
     const int i = blockIdx.x * blockDim.x + q[threadIdx.x];
@@ -411,7 +437,11 @@ __global__ void __launch_bounds__(256) v2_border_kernel(const u64* __restrict__ 
         i = W.list_con[t];
     } else {                                             // every non-core point, compacted into dense warps
         const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
-        const bool todo = i0 < n_items && !(keys[i0] >> 63);
+        bool todo = i0 < n_items && !(keys[i0] >> 63);
+        if (todo) {                                         // no core point in the 3 x 3 cells around it: cannot be a border point
+            const u64 k0 = keys[i0];
+            todo = cb_any_core_near(W.corebits, (u32)(k0 >> P.sshift), ((u32)(k0 >> P.be) & P.umask) / (u32)P.eps);
+        }
         if ((int)threadIdx.x >= cta_compact(todo, q, &s_n)) return;
         i = blockIdx.x * blockDim.x + q[threadIdx.x];
     }
@@ -481,6 +511,8 @@ int index_dbscan(cloops_index* ix, int minPts, int variant, int* d_labels, int* 
     RET_IF(tmp.alloc(&W.flags, (size_t)P.n + 1));
     RET_IF(tmp.alloc(&W.ids, (size_t)P.n + 1));
     RET_IF(tmp.alloc(&W.counters, 8 + 2 * CTR_SLOTS * CTR_STRIDE));
+    int* d_scan_tmp;
+    RET_IF(tmp.alloc(&d_scan_tmp, scan_tmp_ints((long long)P.n + 1)));
     W.chead = W.cellmin = W.list_und = W.list_con = nullptr;
     const bool v2 = variant == CLOOPS_V2;
     if (v2) {
@@ -493,17 +525,15 @@ int index_dbscan(cloops_index* ix, int minPts, int variant, int* d_labels, int* 
     W.slots_core = W.counters + 8;
     W.slots_lab = W.counters + 8 + CTR_SLOTS * CTR_STRIDE;
     CU_TRY(cudaMemsetAsync(W.flags, 0, ((size_t)P.n + 1) * sizeof(int), st));
+    RET_IF(tmp.alloc(&W.corebits, CB_WORDS));
+    CU_TRY(cudaMemsetAsync(W.corebits, 0, (size_t)CB_WORDS * sizeof(u32), st));
 
     stage_mark("workspace", st);                 // allocations + the two memsets above, so that "region_query" times the kernel alone
     RET_IF(index_count(ix, minPts, W.cnt, st));
     stage_mark("region_query", st);
     LAUNCH(flag_kernel, g, 256, 0, st, ix->keys, P, minPts, W, v2 ? 1 : 0);
     if (v2) {
-        size_t scan_bytes = 0;
-        CU_TRY(cub::DeviceScan::InclusiveScan(nullptr, scan_bytes, W.chead, W.chead, cub::Max(), na, st));
-        void* d_scan;
-        RET_IF(tmp.alloc((char**)&d_scan, scan_bytes));
-        CU_TRY(cub::DeviceScan::InclusiveScan(d_scan, scan_bytes, W.chead, W.chead, cub::Max(), na, st));
+        RET_IF((device_scan<SCAN_MAX, true, false>(W.chead, W.chead, na, d_scan_tmp, st)));
         LAUNCH(cellmin_kernel, g, 256, 0, st, ix->rows, P, W);
     }
     stage_mark("flags_cells", st);
@@ -516,22 +546,12 @@ int index_dbscan(cloops_index* ix, int minPts, int variant, int* d_labels, int* 
         int* next_head;                            // next_head[i] = first chain head with index > i (or n_act)
         RET_IF(tmp.alloc(&next_head, (size_t)na + 1));
         LAUNCH(chain_head_kernel, g, 256, 0, st, ix->keys, ix->sstart, P, head, nh_in);
-        size_t scan_bytes = 0;
-        CU_TRY(cub::DeviceScan::InclusiveScan(nullptr, scan_bytes, head, chain, cub::Max(), na, st));
-        void* d_scan;
-        RET_IF(tmp.alloc((char**)&d_scan, scan_bytes));
-        CU_TRY(cub::DeviceScan::InclusiveScan(d_scan, scan_bytes, head, chain, cub::Max(), na, st));
+        RET_IF((device_scan<SCAN_MAX, true, false>(head, chain, na, d_scan_tmp, st)));
         CU_TRY(cudaMemcpyAsync(W.parent, chain, (size_t)na * sizeof(int), cudaMemcpyDeviceToDevice, st));
         {
             // suffix-min over (head ? index : INT_MAX), shifted by one: scan the reversed range
             LAUNCH(fill_int_kernel, 1, 32, 0, st, next_head + na, na, 1LL);
-            auto rin = thrust::make_reverse_iterator(nh_in + na);
-            auto rout = thrust::make_reverse_iterator(next_head + na);
-            size_t b2 = 0;
-            CU_TRY(cub::DeviceScan::InclusiveScan(nullptr, b2, rin, rout, cub::Min(), na, st));
-            void* d_s2;
-            RET_IF(tmp.alloc((char**)&d_s2, b2));
-            CU_TRY(cub::DeviceScan::InclusiveScan(d_s2, b2, rin, rout, cub::Min(), na, st));
+            RET_IF((device_scan<SCAN_MIN, true, true>(nh_in, next_head, na, d_scan_tmp, st)));      // suffix minimum
             LAUNCH(clamp_next_head_kernel, g, 256, 0, st, next_head, na);
             CU_TRY(cudaMemsetAsync(W.ncore, 0, (size_t)na * sizeof(int), st));
         }
@@ -574,13 +594,7 @@ int index_dbscan(cloops_index* ix, int minPts, int variant, int* d_labels, int* 
         stage_mark("survival", st);
     }
     LAUNCH(number_flags_kernel, g, 256, 0, st, ix->keys, P, W, variant);
-    {
-        size_t scan_bytes = 0;
-        CU_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, W.flags, W.ids, P.n + 1, st));
-        void* d_scan;
-        RET_IF(tmp.alloc((char**)&d_scan, scan_bytes));
-        CU_TRY(cub::DeviceScan::ExclusiveSum(d_scan, scan_bytes, W.flags, W.ids, P.n + 1, st));
-    }
+    RET_IF((device_scan<SCAN_ADD, false, false>(W.flags, W.ids, (long long)P.n + 1, d_scan_tmp, st)));
     LAUNCH(label_kernel, g, 256, 0, st, ix->rows, P, W, variant, minPts, d_labels, d_labels_sorted);
     stage_mark("labels", st);
     if (h_info) {

@@ -13,6 +13,7 @@
 #include <cub/cub.cuh>
 
 #include "index.cuh"
+#include "scan.cuh"
 
 namespace cloops {
 
@@ -468,11 +469,9 @@ int index_build(const int32_t* d_x, const int32_t* d_y, int64_t n, int32_t eps, 
         LAUNCH(pack_kernel<true>, cdiv(n, 1024), 256, 0, st, d_x, d_y, cut, P, k0, r0, cnt, reinterpret_cast<int*>(d_sumsq + 2));
         stage_mark("pack", st);
         LAUNCH(strip_sumsq_kernel, std::min(cdiv(P.ns + 3, 256), 148 * 8), 256, 0, st, cnt, P.ns + 3, d_sumsq);
-        size_t scan_bytes = 0;
-        CU_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, cnt, cnt, P.ns + 3, st));
-        void* d_scan;
-        RET_IF(tmp.alloc((char**)&d_scan, scan_bytes));
-        CU_TRY(cub::DeviceScan::ExclusiveSum(d_scan, scan_bytes, cnt, cnt, P.ns + 3, st));
+        int* d_scan;
+        RET_IF(tmp.alloc(&d_scan, scan_tmp_ints(P.ns + 3)));
+        RET_IF((device_scan<SCAN_ADD, false, false>(cnt, cnt, P.ns + 3, d_scan, st)));
         unsigned long long sumsq[2] = {0, 0};
         CU_TRY(cudaMemcpyAsync(sumsq, d_sumsq, sizeof(sumsq), cudaMemcpyDeviceToHost, st));
         CU_TRY(cudaStreamSynchronize(st));

@@ -5,9 +5,8 @@
 // build (two radix sorts, independent of the clustering) runs on a side stream.
 #include <limits.h>
 
-#include <cub/cub.cuh>
-
 #include "index.cuh"
+#include "scan.cuh"
 
 struct cloops_coverage;
 
@@ -163,11 +162,9 @@ static int pass_run(cloops_pass* p, const int32_t* d_x, const int32_t* d_y, int6
             if ((rc = dalloc(&p->cand, (size_t)4 * k, st)) || (rc = dalloc(&p->counts, (size_t)123 * k, st)) || (rc = dalloc(&p->d_m, 1, st))) break;
             cand_flag_kernel<<<cdiv(k, 256), 256, 0, st>>>(p->kind, k, flag);
             g_launches.fetch_add(1);
-            size_t bytes = 0;
-            cub::DeviceScan::ExclusiveSum(nullptr, bytes, flag, pos, k, st);
-            void* d_scan;
-            if ((rc = tmp.alloc((char**)&d_scan, bytes))) break;
-            cub::DeviceScan::ExclusiveSum(d_scan, bytes, flag, pos, k, st);
+            int* d_scan;
+            if ((rc = tmp.alloc(&d_scan, scan_tmp_ints(k)))) break;
+            if ((rc = device_scan<SCAN_ADD, false, false>(flag, pos, k, d_scan, st))) break;
             cand_scatter_kernel<<<cdiv(k, 256), 256, 0, st>>>(p->kind, pos, p->bbox, k, p->cand, p->d_m);
             g_launches.fetch_add(1);
             CU_BRK(cudaStreamWaitEvent(st, side->join, 0));      // join: coverage model ready

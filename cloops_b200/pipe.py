@@ -240,7 +240,15 @@ def _combine_rounds(rounds):
     return allr[keep.view(bool)]
 
 
-def _rounds(cfs, eps, minPts, cut, max_cut, log, weights=None):
+def _finalize_records(e, cut):
+    """combineTwice over the chromosome's rounds + filterClusterByDis (pipe.py:155-174,130-143) -> e["records"] int64 [K,4]."""
+    if "rounds" in e:
+        r = _combine_rounds(e.pop("rounds")).astype(np.int64)
+        e["records"] = r[(r[:, 2] + r[:, 3]) // 2 - (r[:, 0] + r[:, 1]) // 2 >= cut]
+    return e
+
+
+def _rounds(cfs, eps, minPts, cut, max_cut, log, weights=None, finalize=True):
     """The round loop of cLoops/pipe.py:247-281: clustering rounds with the distance cut-off fed forward, candidates of all
     rounds merged (combineTwice) and filtered by the final cut-off.  -> (dataI of this rank's chromosomes with records as
     int64 arrays [K,4] and "first" = first round that produced the chromosome, final cut)"""
@@ -261,9 +269,9 @@ def _rounds(cfs, eps, minPts, cut, max_cut, log, weights=None):
             cut = cut_2
     cuts = [c for c in cuts if c > 0]
     cut = np.max(cuts) if max_cut else np.min(cuts)
-    for key, e in dataI.items():
-        r = _combine_rounds(e.pop("rounds")).astype(np.int64)
-        e["records"] = r[(r[:, 2] + r[:, 3]) // 2 - (r[:, 0] + r[:, 1]) // 2 >= cut]      # filterClusterByDis, pipe.py:130-143
+    if finalize:
+        for e in dataI.values():
+            _finalize_records(e, cut)
     return dataI, cut
 
 
@@ -381,19 +389,26 @@ def call_loops(cfs, eps, minPts, hic=0, cut=0, max_cut=False, weights=None, tail
     range counts, and -- ``tail=True`` -- the statistics tail and the marked loop table.  ``cfs`` lists ALL chromosomes
     (every rank), ``weights`` their PET counts; each rank works on its own share.
     -> dict(cut, dataI, counted, table)"""
-    dataI, cut = _rounds(cfs, eps, minPts, cut, max_cut, _log(), weights)
+    from concurrent.futures import ThreadPoolExecutor
+    dataI, cut = _rounds(cfs, eps, minPts, cut, max_cut, _log(), weights, finalize=False)
     for k, f in enumerate(cfs):
         key = tuple(os.path.split(f)[1].replace("mem:", "").replace(".jd", "").split("-"))
         if key in dataI:
             dataI[key]["order"] = k
     out = {"cut": int(cut), "dataI": dataI, "counted": None, "table": None}
-    if not tail:
-        out["counted"] = _count(dataI, minPts, 0, _local=True)
-        return out
-    # the statistics tail of one chromosome (host threads) runs while the GPU counts the next one
-    from concurrent.futures import ThreadPoolExecutor
-    with ThreadPoolExecutor(max_workers=max(1, min(6, (os.cpu_count() or 2) // 2))) as ex:
-        futs = {k: ex.submit(cModel.tableFromCounts, cModel.countCandidates(dataI[k]["f"], dataI[k]["records"], minPts, 0)) for k in dataI}
+    # candidate merging of chromosome k+1 (host C++, releases the GIL) runs while the GPU counts chromosome k; with
+    # ``tail`` the statistics tail of a chromosome (host threads) runs while the GPU counts the next ones
+    with ThreadPoolExecutor(max_workers=1) as prep, ThreadPoolExecutor(max_workers=max(1, min(6, (os.cpu_count() or 2) // 2))) as ex:
+        ready = {k: prep.submit(_finalize_records, dataI[k], cut) for k in dataI}
+        counted, futs = {}, {}
+        for k in dataI:
+            ready[k].result()
+            counted[k] = cModel.countCandidates(dataI[k]["f"], dataI[k]["records"], minPts, 0)
+            if tail:
+                futs[k] = ex.submit(cModel.tableFromCounts, counted[k])
+        if not tail:
+            out["counted"] = counted
+            return out
         tables = {k: f.result() for k, f in futs.items()}
     ds = _tables(dataI, tables, _local=True, done=True)
     if ds is not None:
