@@ -369,14 +369,16 @@ __global__ void __launch_bounds__(256) v2_reset_kernel(Work W, int n_und) {
 // around it, and the core points of one cell are mutual neighbours (one component per cell, cDBSCAN2.py:80-83) -- so the
 // distinct adjacent components fit a fixed register list and every neighbour is looked at once.
 #define ADJ_MAX 9
-__global__ void __launch_bounds__(128) v2_accumulate_kernel(const u64* __restrict__ keys, const int* __restrict__ sstart,
-                                                            GridParams P, Work W, int n_con) {
+// The distinct components adjacent to every contested border point, gathered ONCE (one neighbour walk per point): the survival
+// rounds and the final re-assignment then work on these short lists (adj[k * n_con + t], adj_n[t]) and only re-read the
+// components' status -- round 1 walked the neighbourhood again in every round.
+__global__ void __launch_bounds__(128) v2_adjacency_kernel(const u64* __restrict__ keys, const int* __restrict__ sstart, GridParams P,
+                                                           Work W, int n_con, int* __restrict__ adj, unsigned char* __restrict__ adj_n) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_con) return;
     const int i = W.list_con[t];
     const PointView p = view(keys[i], P);
-    int roots[ADJ_MAX], ranks[ADJ_MAX];
-    unsigned undecided = 0;                     // bit k: roots[k] is undecided (else alive)
+    int roots[ADJ_MAX];
     int n_adj = 0;
     RootCache rc;
     for_each_neighbour(keys, sstart, P, i, p, [&](int j, u64 kq) {
@@ -384,22 +386,42 @@ __global__ void __launch_bounds__(128) v2_accumulate_kernel(const u64* __restric
         const int before = rc.last_parent;
         rc.lookup(W, j);
         if (rc.last_parent == before) return true;          // same component as the previous core neighbour
-        if (rc.status == ST_DEAD) return true;
         bool dup = false;
 #pragma unroll
         for (int k = 0; k < ADJ_MAX; ++k) dup |= (k < n_adj && roots[k] == rc.root);
         if (dup || n_adj >= ADJ_MAX) return true;
 #pragma unroll
         for (int k = 0; k < ADJ_MAX; ++k)
-            if (k == n_adj) { roots[k] = rc.root; ranks[k] = rc.rank; }
-        undecided |= (rc.status == ST_UNDECIDED ? 1u : 0u) << n_adj;
+            if (k == n_adj) roots[k] = rc.root;
         ++n_adj;
         return true;
     });
-    int min_nd_rank = INT_MAX, min_nd = -1, min_alive_rank = INT_MAX;
+#pragma unroll
+    for (int k = 0; k < ADJ_MAX; ++k)
+        if (k < n_adj) adj[(size_t)k * n_con + t] = roots[k];
+    adj_n[t] = (unsigned char)n_adj;
+}
+
+__global__ void __launch_bounds__(128) v2_accumulate_kernel(Work W, int n_con, const int* __restrict__ adj, const unsigned char* __restrict__ adj_n) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_con) return;
+    const int n_adj = adj_n[t];
+    int roots[ADJ_MAX], ranks[ADJ_MAX];
+    unsigned undecided = 0, live = 0;           // bit k: roots[k] is undecided / not dead
 #pragma unroll
     for (int k = 0; k < ADJ_MAX; ++k) {
         if (k >= n_adj) continue;
+        const int r = adj[(size_t)k * n_con + t];
+        const unsigned char st = W.status[r];
+        roots[k] = r;
+        ranks[k] = W.rank[r];
+        if (st != ST_DEAD) live |= 1u << k;
+        if (st == ST_UNDECIDED) undecided |= 1u << k;
+    }
+    int min_nd_rank = INT_MAX, min_nd = -1, min_alive_rank = INT_MAX;
+#pragma unroll
+    for (int k = 0; k < ADJ_MAX; ++k) {
+        if (k >= n_adj || !((live >> k) & 1u)) continue;
         if (ranks[k] < min_nd_rank) { min_nd_rank = ranks[k]; min_nd = k; }
         if (!((undecided >> k) & 1u) && ranks[k] < min_alive_rank) min_alive_rank = ranks[k];
     }
@@ -410,6 +432,23 @@ __global__ void __launch_bounds__(128) v2_accumulate_kernel(const u64* __restric
         if (k == min_nd) atomicAdd(&W.size[roots[k]], 1);
         if (ranks[k] < min_alive_rank) atomicAdd(&W.ub[roots[k]], 1);      // every distinct undecided component ranked below the best alive one
     }
+}
+
+// final owner of the contested points once every component is decided: the lowest-ranked adjacent component that lives
+__global__ void __launch_bounds__(256) v2_reassign_kernel(Work W, int n_con, const int* __restrict__ adj, const unsigned char* __restrict__ adj_n) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_con) return;
+    const int n_adj = adj_n[t];
+    int best_rank = INT_MAX, best_root = -1;
+#pragma unroll
+    for (int k = 0; k < ADJ_MAX; ++k) {
+        if (k >= n_adj) continue;
+        const int r = adj[(size_t)k * n_con + t];
+        if (W.status[r] == ST_DEAD) continue;
+        const int rk = W.rank[r];
+        if (rk < best_rank) { best_rank = rk; best_root = r; }
+    }
+    W.assigned[W.list_con[t]] = best_root;
 }
 
 __global__ void __launch_bounds__(256) v2_decide_kernel(Work W, int n_und, int minPts) {
@@ -577,9 +616,16 @@ int index_dbscan(cloops_index* ix, int minPts, int variant, int* d_labels, int* 
         CU_TRY(cudaStreamSynchronize(st));
         const int n_und = counters[0], n_con = counters[1];
         if (n_und > 0) {
+            int* adj = nullptr;
+            unsigned char* adj_n = nullptr;
+            if (n_con > 0) {
+                RET_IF(tmp.alloc(&adj, (size_t)ADJ_MAX * n_con));
+                RET_IF(tmp.alloc(&adj_n, (size_t)n_con));
+                LAUNCH(v2_adjacency_kernel, cdiv(n_con, 128), 128, 0, st, ix->keys, ix->sstart, P, W, n_con, adj, adj_n);
+            }
             for (int round = 0;; ++round) {
                 LAUNCH(v2_reset_kernel, cdiv(n_und, 256), 256, 0, st, W, n_und);
-                if (n_con > 0) LAUNCH(v2_accumulate_kernel, cdiv(n_con, 128), 128, 0, st, ix->keys, ix->sstart, P, W, n_con);
+                if (n_con > 0) LAUNCH(v2_accumulate_kernel, cdiv(n_con, 128), 128, 0, st, W, n_con, adj, adj_n);
                 LAUNCH(v2_decide_kernel, cdiv(n_und, 256), 256, 0, st, W, n_und, minPts);
                 CU_TRY(cudaMemcpyAsync(counters, W.counters, sizeof(counters), cudaMemcpyDeviceToHost, st));
                 CU_TRY(cudaStreamSynchronize(st));
@@ -588,7 +634,7 @@ int index_dbscan(cloops_index* ix, int minPts, int variant, int* d_labels, int* 
                 if (round > na) return fail(CLOOPS_ECUDA, "v2 survival did not converge");
             }
             if (n_con > 0 && counters[3] > 0)
-                LAUNCH(v2_border_kernel<true>, cdiv(n_con, 256), 256, 0, st, ix->keys, ix->sstart, P, W, n_con);
+                LAUNCH(v2_reassign_kernel, cdiv(n_con, 256), 256, 0, st, W, n_con, adj, adj_n);
             if (g_trace) fprintf(stderr, "[cloops] v2 survival: n_act=%d undecided=%d contested=%d rounds=%d dead=%d\n", na, n_und, n_con, g_trace_rounds, counters[3]);
         }
         stage_mark("survival", st);

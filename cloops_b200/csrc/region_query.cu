@@ -167,7 +167,7 @@ __device__ __forceinline__ u32 uniform_lower_bound(u32 pa, u32 t, int nsteps, u3
 
 // points of an adjacent strip with W in [tlo,thi] that pass the v test; counting stops at `room`.
 // sa = address of the word before the strip's first W; dv = byte distance from the W array to the V array.
-template <bool NEXT>
+template <bool NEXT, int PROBES>
 __device__ __forceinline__ int adjacent_count(u32 sa, u32 dv, u32 tlo, u32 thi, u32 vm, int nsteps, u32 last_a, int room) {
     const u32 ja = uniform_lower_bound(sa, tlo, nsteps, last_a);
     const u32 w0 = lds_off<0>(ja);
@@ -186,8 +186,26 @@ __device__ __forceinline__ int adjacent_count(u32 sa, u32 dv, u32 tlo, u32 thi, 
             inc_in_window_ge(f, lds_off<8>(ja), thi, lds_off<8>(va), vm);
             inc_in_window_ge(f, w3, thi, lds_off<12>(va), vm);
         }
-        if (w3 <= thi) {                                                   // rare: more than four points in the window
-            for (u32 a = ja + 16u; f < room && lds_off<0>(a) <= thi; a += 4u) {
+        u32 wl = w3;
+        u32 next_a = ja + 16u;
+        if (PROBES == 8 && w3 <= thi) {            // caps >= 10 (Hi-C): windows of 5-8 points are common, four more straight-line probes
+            const u32 w7 = lds_off<28>(ja);
+            if (NEXT) {
+                inc_in_window_le(f, lds_off<16>(ja), thi, lds_off<16>(va), vm);
+                inc_in_window_le(f, lds_off<20>(ja), thi, lds_off<20>(va), vm);
+                inc_in_window_le(f, lds_off<24>(ja), thi, lds_off<24>(va), vm);
+                inc_in_window_le(f, w7, thi, lds_off<28>(va), vm);
+            } else {
+                inc_in_window_ge(f, lds_off<16>(ja), thi, lds_off<16>(va), vm);
+                inc_in_window_ge(f, lds_off<20>(ja), thi, lds_off<20>(va), vm);
+                inc_in_window_ge(f, lds_off<24>(ja), thi, lds_off<24>(va), vm);
+                inc_in_window_ge(f, w7, thi, lds_off<28>(va), vm);
+            }
+            wl = w7;
+            next_a = ja + 32u;
+        }
+        if (wl <= thi) {                                                   // rare: more points in the window than were probed
+            for (u32 a = next_a; f < room && lds_off<0>(a) <= thi; a += 4u) {
                 const u32 v = lds_off<0>(a + dv);
                 f += (NEXT ? v <= vm : v >= vm) ? 1 : 0;
             }
@@ -339,8 +357,8 @@ __global__ void __launch_bounds__(CT_THREADS) count_kernel_tiled(const u64* __re
             const u32 pa = w_a + 4u * (u32)(sl0 + t0 + pt);
             const u32 wp = lds_off<0>(pa), vm = lds_off<0>(pa + dv);
             const int srel = (int)(wp >> bu);
-            c += adjacent_count<false>(w_a + 4u * (u32)S[srel - 1] - 4u, dv, wp - one - eps, wp - one + eps, vm, nsteps, last_a, cap - c);
-            if (c < cap) c += adjacent_count<true>(w_a + 4u * (u32)S[srel + 1] - 4u, dv, wp + one - eps, wp + one + eps, vm, nsteps, last_a, cap - c);
+            c += adjacent_count<false, (CAPT == 0 ? 8 : 4)>(w_a + 4u * (u32)S[srel - 1] - 4u, dv, wp - one - eps, wp - one + eps, vm, nsteps, last_a, cap - c);
+            if (c < cap) c += adjacent_count<true, (CAPT == 0 ? 8 : 4)>(w_a + 4u * (u32)S[srel + 1] - 4u, dv, wp + one - eps, wp + one + eps, vm, nsteps, last_a, cap - c);
             cnt[t0 + pt] = min(c, cap);
         }
     }
