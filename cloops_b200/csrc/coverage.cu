@@ -247,6 +247,134 @@ __global__ void __launch_bounds__(32 * RC_WARPS) range_count_ranked_kernel(const
     for (int t = lane; t < NOUT; t += 32) out[m * NOUT + t] = O[t];
 }
 
+// ---- the same counts with one CTA per candidate (WIN = 5) -------------------------------------------------------------
+// One warp per candidate leaves the launch waiting for its largest candidates (a loop whose anchors hold 10^5 PETs keeps a
+// single warp busy for milliseconds while the SMs drain).  Here RT_THREADS threads share a candidate: the rank searches are
+// spread over the threads, every range is walked with a CTA-wide stride, and the counters are shared-memory atomics fed by
+// warp-reduced partial sums.  Same arithmetic as range_count_ranked_kernel.
+#define RT_THREADS 256
+template <int WIN>
+__global__ void __launch_bounds__(RT_THREADS) range_count_team_kernel(const int* __restrict__ xs_x, const int* __restrict__ xs_y,
+                                                                      const int* __restrict__ ys_y, const int* __restrict__ ys_x, int n,
+                                                                      const int* __restrict__ cand, long long ncand,
+                                                                      const int* __restrict__ d_ncand, int* __restrict__ out) {
+    constexpr int NOUT = (WIN > 0) ? 123 : 3;
+    constexpr int NWIN = (WIN > 0) ? NW : 1;
+    __shared__ Windows W;
+    __shared__ int R[4 * RQ_NW];
+    __shared__ int both[RQ_NW];
+    __shared__ int O[NOUT];
+    __shared__ int hs[4 + 4];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const long long m = blockIdx.x;
+    if (m >= ncand || (d_ncand && m >= *d_ncand)) return;      // whole CTA
+    if (tid == 0) {
+        const int4 c = __ldg(reinterpret_cast<const int4*>(cand) + m);
+        make_windows(c.x, c.y, c.z, c.w, WIN, W);
+    }
+    for (int t = tid; t < NOUT; t += RT_THREADS) O[t] = 0;
+    if (tid < RQ_NW) both[tid] = 0;
+    __syncthreads();
+    const int nh = W.nh;
+    if (tid < 4) {                                             // X lo, X hi, Y lo, Y hi of the span of all windows
+        const int g0 = W.h0[0], g1 = W.h1[nh - 1];
+        hs[tid] = tid == 0 ? lb_exact(xs_x, 0, n, g0) : (tid == 1 ? ub_exact(xs_x, 0, n, g1) : (tid == 2 ? lb_exact(ys_y, 0, n, g0) : ub_exact(ys_y, 0, n, g1)));
+    } else if (WIN > 0 && tid >= 32 && tid < 32 + 2 * nh) {    // X ranges of the hull(s) for the joint walk
+        const int h = (tid - 32) >> 1;
+        hs[4 + (tid - 32)] = ((tid - 32) & 1) ? ub_exact(xs_x, 0, n, W.h1[h]) : lb_exact(xs_x, 0, n, W.h0[h]);
+    }
+    __syncthreads();
+    if (tid < 4 * NWIN) {
+        const int view = tid & 1, wi = tid >> 1;
+        const int fam = wi >= NWIN, w = fam ? wi - NWIN : wi;
+        const int w0 = fam ? W.b0[w] : W.a0[w], w1 = fam ? W.b1[w] : W.a1[w];
+        int lo = 0, hi = 0;
+        if (w0 <= w1) {
+            const int* __restrict__ a = view ? ys_y : xs_x;
+            lo = lb_exact(a, view ? hs[2] : hs[0], view ? hs[3] : hs[1], w0);
+            hi = ub_exact(a, lo, view ? hs[3] : hs[1], w1);
+        }
+        R[4 * (fam * NW + w) + 2 * view] = lo;
+        R[4 * (fam * NW + w) + 2 * view + 1] = hi;
+    }
+    __syncthreads();
+    // window sizes: PETs of the X range whose partner lies in the same window; rab on the way
+    for (int wi = 0; wi < 2 * NWIN; ++wi) {
+        const int fam = wi >= NWIN, w = fam ? wi - NWIN : wi;
+        const int* r = R + 4 * (fam * NW + w);
+        const int lo = r[0], hi = r[1];
+        const int2 own = fam ? W.B[w] : W.A[w];
+        const int2 b0w = W.B[0];
+        int cb = 0, rab = 0;
+        for (int t = lo + tid; t < hi; t += RT_THREADS) {
+            const int y = __ldg(xs_y + t);
+            cb += ((unsigned)(y - own.x) <= (unsigned)own.y) ? 1 : 0;
+            if (wi == 0) rab += ((unsigned)(y - b0w.x) <= (unsigned)b0w.y) ? 1 : 0;
+        }
+        cb = __reduce_add_sync(0xffffffffu, cb);
+        if (lane == 0 && cb) atomicAdd(&both[fam * NW + w], cb);
+        if (wi == 0) {
+            rab = __reduce_add_sync(0xffffffffu, rab);
+            if (lane == 0 && rab) atomicAdd(&O[2], rab);
+        }
+    }
+    // joint table (as range_count_ranked_kernel, CTA-wide stride)
+    if (WIN > 0) {
+        int* J = O + 23;
+        const int fa0 = W.fa0, fa1 = W.fa1, fb0 = W.fb0, fb1 = W.fb1;
+        const int i0 = max(fa0, fb0), i1 = min(fa1, fb1);
+        for (int pass = 0; pass <= nh; ++pass) {
+            int lo, hi;
+            const bool via_y = pass == nh;
+            if (!via_y) {
+                lo = hs[4 + 2 * pass];
+                hi = hs[4 + 2 * pass + 1];
+            } else {
+                if (i0 > i1) break;
+                lo = lb_exact(ys_y, hs[2], hs[3], i0);
+                hi = ub_exact(ys_y, lo, hs[3], i1);
+            }
+            const int* __restrict__ px = via_y ? ys_x : xs_x;
+            const int* __restrict__ py = via_y ? ys_y : xs_y;
+            for (int t = lo + tid; t < hi; t += RT_THREADS) {
+                const int x = __ldg(px + t), y = __ldg(py + t);
+                bool xa = x >= fa0 && x <= fa1, xb = x >= fb0 && x <= fb1;
+                if (via_y) {
+                    bool seen = false;
+                    for (int g = 0; g < nh; ++g) seen |= (x >= W.h0[g] && x <= W.h1[g]);
+                    if (seen) continue;
+                    xa = xb = false;
+                }
+                const bool ya = y >= fa0 && y <= fa1, yb = y >= fb0 && y <= fb1;
+                if (!(xa || ya) || !(xb || yb)) continue;
+                unsigned ma = 0, mb = 0;
+                if (xa) ma |= window_mask(W.A, NW, x);
+                if (ya) ma |= window_mask(W.A, NW, y);
+                ma >>= 1;
+                if (ma == 0) continue;
+                if (xb) mb |= window_mask(W.B, NW, x);
+                if (yb) mb |= window_mask(W.B, NW, y);
+                mb >>= 1;
+                for (unsigned rr = ma; rr; rr &= rr - 1) {
+                    const int i = __ffs(rr) - 1;
+                    for (unsigned q = mb; q; q &= q - 1) atomicAdd(&J[10 * i + (__ffs(q) - 1)], 1);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int t = tid; t < NOUT; t += RT_THREADS) {
+        int v = O[t];
+        if (t < 2) v = (R[4 * (t * NW) + 1] - R[4 * (t * NW)]) + (R[4 * (t * NW) + 3] - R[4 * (t * NW) + 2]) - both[t * NW];
+        else if (t >= 3 && t < 23) {
+            const int fam = t >= 13, w = fam ? t - 12 : t - 2;
+            const int* r = R + 4 * (fam * NW + w);
+            v = (r[1] - r[0]) + (r[3] - r[2]) - both[fam * NW + w];
+        }
+        out[m * NOUT + t] = v;
+    }
+}
+
 // ---- legacy form (round 1; CLOOPS_RC=legacy for A/B runs) ------------------------------------------------------------
 // One WARP per candidate (4 candidates per CTA), no CTA-wide barriers: lane 0 derives the windows, up to
 // 8 lanes run the slice binary searches, then the 32 lanes stride over the X-sorted and Y-sorted slices.
@@ -384,6 +512,10 @@ int coverage_build(const int32_t* d_x, const int32_t* d_y, int64_t n, cloops_cov
 // CLOOPS_RC=legacy selects the round-1 walk for A/B runs.  Measured on the config-4 step (437 k scored candidates of 1.23 M,
 // anchors ~19 kb wide, mostly overlapping A / B hulls): 123 integers 260 -> 148 ms per step, (ra, rb, rab) of all candidates
 // 60.5 -> 8.9 ms per step (profiles/r02_bench_c4_ranked.json / _legacy.json).
+static bool rc_team() {                       // CLOOPS_RC=warp: one warp per candidate also for the 123 integers (A/B)
+    static const bool v = !(getenv("CLOOPS_RC") != nullptr && strcmp(getenv("CLOOPS_RC"), "warp") == 0);
+    return v;
+}
 static bool rc_legacy(int win = 5) {
     static const bool v = getenv("CLOOPS_RC") != nullptr && strcmp(getenv("CLOOPS_RC"), "legacy") == 0;
     (void)win;
@@ -395,8 +527,10 @@ int range_counts_dev(const cloops_coverage* cov, const int32_t* d_cand, int64_t 
     if (ncand <= 0) return 0;
     if (cov->n == 0) { CU_TRY(cudaMemsetAsync(d_out, 0, (size_t)ncand * 123 * sizeof(int), st)); return 0; }
     if (!rc_legacy()) {
-        LAUNCH(range_count_ranked_kernel<5>, (unsigned)((ncand + RC_WARPS - 1) / RC_WARPS), 32 * RC_WARPS, 0, st, cov->xs_x, cov->xs_y,
-               cov->ys_y, cov->ys_x, cov->n, d_cand, (long long)ncand, d_ncand, d_out);
+        if (rc_team()) LAUNCH(range_count_team_kernel<5>, (unsigned)ncand, RT_THREADS, 0, st, cov->xs_x, cov->xs_y, cov->ys_y, cov->ys_x, cov->n, d_cand,
+                              (long long)ncand, d_ncand, d_out);
+        else LAUNCH(range_count_ranked_kernel<5>, (unsigned)((ncand + RC_WARPS - 1) / RC_WARPS), 32 * RC_WARPS, 0, st, cov->xs_x, cov->xs_y,
+                    cov->ys_y, cov->ys_x, cov->n, d_cand, (long long)ncand, d_ncand, d_out);
         return 0;
     }
     LAUNCH(range_count_kernel<5>, (unsigned)((ncand + RC_WARPS - 1) / RC_WARPS), 32 * RC_WARPS, 0, st, cov->xs_x, cov->xs_y, cov->ys_y,
@@ -441,6 +575,7 @@ int cloops_range_counts(const cloops_coverage* cov, const int32_t* d_cand, int64
     stages_begin(st);
     if (m > 0) {
         if (cov->n == 0) CU_TRY(cudaMemsetAsync(d_out, 0, (size_t)m * 123 * sizeof(int), st));
+        else if (!rc_legacy() && rc_team()) LAUNCH(range_count_team_kernel<5>, (unsigned)m, RT_THREADS, 0, st, cov->xs_x, cov->xs_y, cov->ys_y, cov->ys_x, cov->n, d_cand, (long long)m, (const int*)nullptr, d_out);
         else if (!rc_legacy()) LAUNCH(range_count_ranked_kernel<5>, (unsigned)((m + RC_WARPS - 1) / RC_WARPS), 32 * RC_WARPS, 0, st, cov->xs_x, cov->xs_y, cov->ys_y, cov->ys_x, cov->n, d_cand, (long long)m, (const int*)nullptr, d_out);
         else LAUNCH(range_count_kernel<5>, (unsigned)((m + RC_WARPS - 1) / RC_WARPS), 32 * RC_WARPS, 0, st, cov->xs_x, cov->xs_y, cov->ys_y, cov->ys_x, cov->n, d_cand, (long long)m, (const int*)nullptr, d_out);
     }
