@@ -252,8 +252,7 @@ __global__ void __launch_bounds__(32 * RC_WARPS) range_count_ranked_kernel(const
 // single warp busy for milliseconds while the SMs drain).  Here RT_THREADS threads share a candidate: the rank searches are
 // spread over the threads, every range is walked with a CTA-wide stride, and the counters are shared-memory atomics fed by
 // warp-reduced partial sums.  Same arithmetic as range_count_ranked_kernel.
-#define RT_THREADS 256
-template <int WIN>
+template <int WIN, int RT_THREADS>
 __global__ void __launch_bounds__(RT_THREADS) range_count_team_kernel(const int* __restrict__ xs_x, const int* __restrict__ xs_y,
                                                                       const int* __restrict__ ys_y, const int* __restrict__ ys_x, int n,
                                                                       const int* __restrict__ cand, long long ncand,
@@ -516,6 +515,15 @@ static bool rc_team() {                       // CLOOPS_RC=warp: one warp per ca
     static const bool v = !(getenv("CLOOPS_RC") != nullptr && strcmp(getenv("CLOOPS_RC"), "warp") == 0);
     return v;
 }
+static int launch_team(const cloops_coverage* cov, const int32_t* d_cand, int64_t ncand, const int* d_ncand, int32_t* d_out, cudaStream_t st) {
+    static const int threads = getenv("CLOOPS_RC_TEAM") ? atoi(getenv("CLOOPS_RC_TEAM")) : 256;      // measurement knob: 128 / 256 / 512
+#define RT_LAUNCH(T) LAUNCH((range_count_team_kernel<5, T>), (unsigned)ncand, T, 0, st, cov->xs_x, cov->xs_y, cov->ys_y, cov->ys_x, cov->n, d_cand, (long long)ncand, d_ncand, d_out)
+    if (threads == 128) RT_LAUNCH(128);
+    else if (threads == 512) RT_LAUNCH(512);
+    else RT_LAUNCH(256);
+#undef RT_LAUNCH
+    return 0;
+}
 static bool rc_legacy(int win = 5) {
     static const bool v = getenv("CLOOPS_RC") != nullptr && strcmp(getenv("CLOOPS_RC"), "legacy") == 0;
     (void)win;
@@ -527,8 +535,7 @@ int range_counts_dev(const cloops_coverage* cov, const int32_t* d_cand, int64_t 
     if (ncand <= 0) return 0;
     if (cov->n == 0) { CU_TRY(cudaMemsetAsync(d_out, 0, (size_t)ncand * 123 * sizeof(int), st)); return 0; }
     if (!rc_legacy()) {
-        if (rc_team()) LAUNCH(range_count_team_kernel<5>, (unsigned)ncand, RT_THREADS, 0, st, cov->xs_x, cov->xs_y, cov->ys_y, cov->ys_x, cov->n, d_cand,
-                              (long long)ncand, d_ncand, d_out);
+        if (rc_team()) RET_IF(launch_team(cov, d_cand, ncand, d_ncand, d_out, st));
         else LAUNCH(range_count_ranked_kernel<5>, (unsigned)((ncand + RC_WARPS - 1) / RC_WARPS), 32 * RC_WARPS, 0, st, cov->xs_x, cov->xs_y,
                     cov->ys_y, cov->ys_x, cov->n, d_cand, (long long)ncand, d_ncand, d_out);
         return 0;
@@ -575,7 +582,7 @@ int cloops_range_counts(const cloops_coverage* cov, const int32_t* d_cand, int64
     stages_begin(st);
     if (m > 0) {
         if (cov->n == 0) CU_TRY(cudaMemsetAsync(d_out, 0, (size_t)m * 123 * sizeof(int), st));
-        else if (!rc_legacy() && rc_team()) LAUNCH(range_count_team_kernel<5>, (unsigned)m, RT_THREADS, 0, st, cov->xs_x, cov->xs_y, cov->ys_y, cov->ys_x, cov->n, d_cand, (long long)m, (const int*)nullptr, d_out);
+        else if (!rc_legacy() && rc_team()) RET_IF(launch_team(cov, d_cand, m, (const int*)nullptr, d_out, st));
         else if (!rc_legacy()) LAUNCH(range_count_ranked_kernel<5>, (unsigned)((m + RC_WARPS - 1) / RC_WARPS), 32 * RC_WARPS, 0, st, cov->xs_x, cov->xs_y, cov->ys_y, cov->ys_x, cov->n, d_cand, (long long)m, (const int*)nullptr, d_out);
         else LAUNCH(range_count_kernel<5>, (unsigned)((m + RC_WARPS - 1) / RC_WARPS), 32 * RC_WARPS, 0, st, cov->xs_x, cov->xs_y, cov->ys_y, cov->ys_x, cov->n, d_cand, (long long)m, (const int*)nullptr, d_out);
     }

@@ -84,8 +84,8 @@ __global__ void __launch_bounds__(32 * RS_NQ) dist_stats_commit_kernel(const dou
     double v = 0;
     for (int b = lane; b < nblocks; b += 32) v += partial[b * RS_NQ + k];
     for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
-    if (lane == 0) mom[k] += v;
-    if (threadIdx.x == 0) mom[8] += 1.0;
+    if (lane == 0) atomicAdd(&mom[k], v);                           // passes of several chromosomes may run on different streams
+    if (threadIdx.x == 0) atomicAdd(&mom[8], 1.0);
 }
 
 // the two middle order statistics of the histogrammed values: out[0] = value of rank (k-1)/2, out[1] = value of rank k/2

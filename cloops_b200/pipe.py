@@ -199,6 +199,42 @@ def _cluster_chrom(f, eps, minPts, cut, acc):
     return key, bbox[kind == 1], int((kind == 2).sum())
 
 
+#: chromosomes of a round in flight at once on this GPU, each on its own CUDA stream and host thread: while one pass waits
+#: for a size it needs on the host (five short synchronisations per pass), the kernels of another keep the SMs busy
+STREAMS = max(1, int(os.environ.get("CLOOPS_STREAMS", "2")))
+_pool = {}
+
+
+def _cluster_many(files, eps, minPts, cut, acc):
+    """_cluster_chrom for every file, results in file order."""
+    import torch
+    if STREAMS <= 1 or len(files) <= 1 or not acc.hist.is_cuda:
+        return [_cluster_chrom(f, eps, minPts, cut, acc) for f in files]
+    from concurrent.futures import ThreadPoolExecutor
+    dev = torch.cuda.current_device()
+    if "ex" not in _pool:
+        _pool["ex"] = ThreadPoolExecutor(max_workers=STREAMS)
+        _pool["streams"] = {}
+    main = torch.cuda.current_stream()
+
+    def work(f):
+        import threading
+        torch.cuda.set_device(dev)
+        tid = threading.get_ident()
+        st = _pool["streams"].get((dev, tid))
+        if st is None:
+            st = _pool["streams"][(dev, tid)] = torch.cuda.Stream(device=dev)
+        st.wait_stream(main)                               # the accumulators were zeroed on the caller's stream
+        with torch.cuda.stream(st):
+            out = _cluster_chrom(f, eps, minPts, cut, acc)
+        return out, st
+
+    res = list(_pool["ex"].map(work, files))
+    for _, st in res:
+        main.wait_stream(st)
+    return [r for r, _ in res]
+
+
 def _round(fs, eps, minPts, cut, weights=None):
     """One clustering round over the chromosomes this rank owns, the distance cut-off reduced on the GPUs.
     -> (dataI_2, n_self_clusters, len(dis), len(dss), cut_2 or None, n_chromosomes_with_inter_ligation_clusters);
@@ -207,8 +243,8 @@ def _round(fs, eps, minPts, cut, weights=None):
     acc = _RoundAcc.get()
     acc.reset()
     dataI, n_self = {}, 0
-    for f in dist.my_share(fs, _weights(fs) if weights is None else weights):
-        key, inter, ns = _cluster_chrom(f, eps, minPts, cut, acc)
+    mine = dist.my_share(fs, _weights(fs) if weights is None else weights)
+    for f, (key, inter, ns) in zip(mine, _cluster_many(mine, eps, minPts, cut, acc)):
         if len(inter) == 0:                                # pipe.py:121-122
             continue
         dataI[key] = {"f": f, "records": inter}
