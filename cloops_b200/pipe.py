@@ -201,15 +201,17 @@ def _cluster_chrom(f, eps, minPts, cut, acc):
 
 #: chromosomes of a round in flight at once on this GPU, each on its own CUDA stream and host thread: while one pass waits
 #: for a size it needs on the host (five short synchronisations per pass), the kernels of another keep the SMs busy
-STREAMS = max(1, int(os.environ.get("CLOOPS_STREAMS", "2")))
+STREAMS = max(1, int(os.environ.get("CLOOPS_STREAMS", "3")))
 _pool = {}
 
 
-def _cluster_many(files, eps, minPts, cut, acc):
-    """_cluster_chrom for every file, results in file order."""
+def _on_streams(items, fn):
+    """[fn(item) for item in items], up to STREAMS of them in flight, each host thread on a CUDA stream of its own (the
+    streams wait for the caller's stream first and the caller's stream waits for them afterwards)."""
     import torch
-    if STREAMS <= 1 or len(files) <= 1 or not acc.hist.is_cuda:
-        return [_cluster_chrom(f, eps, minPts, cut, acc) for f in files]
+    items = list(items)
+    if STREAMS <= 1 or len(items) <= 1 or not torch.cuda.is_available():
+        return [fn(it) for it in items]
     from concurrent.futures import ThreadPoolExecutor
     dev = torch.cuda.current_device()
     if "ex" not in _pool:
@@ -217,22 +219,29 @@ def _cluster_many(files, eps, minPts, cut, acc):
         _pool["streams"] = {}
     main = torch.cuda.current_stream()
 
-    def work(f):
+    def work(it):
         import threading
         torch.cuda.set_device(dev)
         tid = threading.get_ident()
         st = _pool["streams"].get((dev, tid))
         if st is None:
             st = _pool["streams"][(dev, tid)] = torch.cuda.Stream(device=dev)
-        st.wait_stream(main)                               # the accumulators were zeroed on the caller's stream
+        st.wait_stream(main)
         with torch.cuda.stream(st):
-            out = _cluster_chrom(f, eps, minPts, cut, acc)
+            out = fn(it)
         return out, st
 
-    res = list(_pool["ex"].map(work, files))
+    res = list(_pool["ex"].map(work, items))
     for _, st in res:
         main.wait_stream(st)
     return [r for r, _ in res]
+
+
+def _cluster_many(files, eps, minPts, cut, acc):
+    """_cluster_chrom for every file, results in file order."""
+    if not acc.hist.is_cuda:
+        return [_cluster_chrom(f, eps, minPts, cut, acc) for f in files]
+    return _on_streams(files, lambda f: _cluster_chrom(f, eps, minPts, cut, acc))
 
 
 def _round(fs, eps, minPts, cut, weights=None):
@@ -436,16 +445,21 @@ def call_loops(cfs, eps, minPts, hic=0, cut=0, max_cut=False, weights=None, tail
     # ``tail`` the statistics tail of a chromosome (host threads) runs while the GPU counts the next ones
     with ThreadPoolExecutor(max_workers=1) as prep, ThreadPoolExecutor(max_workers=max(1, min(6, (os.cpu_count() or 2) // 2))) as ex:
         ready = {k: prep.submit(_finalize_records, dataI[k], cut) for k in dataI}
-        counted, futs = {}, {}
-        for k in dataI:
+        futs = {}
+
+        def count_one(k):
             ready[k].result()
-            counted[k] = cModel.countCandidates(dataI[k]["f"], dataI[k]["records"], minPts, 0)
+            c = cModel.countCandidates(dataI[k]["f"], dataI[k]["records"], minPts, 0)
             if tail:
-                futs[k] = ex.submit(cModel.tableFromCounts, counted[k])
+                futs[k] = ex.submit(cModel.tableFromCounts, c)
+            return c
+
+        keys = list(dataI)
+        counted = dict(zip(keys, _on_streams(keys, count_one)))
         if not tail:
             out["counted"] = counted
             return out
-        tables = {k: f.result() for k, f in futs.items()}
+        tables = {k: futs[k].result() for k in keys}
     ds = _tables(dataI, tables, _local=True, done=True)
     if ds is not None:
         out["table"] = (markIntSigHic(ds) if hic else markIntSig(ds)) if mark else ds
