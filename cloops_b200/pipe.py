@@ -201,7 +201,7 @@ def _cluster_chrom(f, eps, minPts, cut, acc):
 
 #: chromosomes of a round in flight at once on this GPU, each on its own CUDA stream and host thread: while one pass waits
 #: for a size it needs on the host (five short synchronisations per pass), the kernels of another keep the SMs busy
-STREAMS = max(1, int(os.environ.get("CLOOPS_STREAMS", "3")))
+STREAMS = max(1, int(os.environ.get("CLOOPS_STREAMS", "4")))
 _pool = {}
 
 
