@@ -168,9 +168,9 @@ def reference_sample(cfg, args, cores, have=None):
         X, Y = have
     else:
         X, Y = synth.chromosome(args.pets, CHROM_LEN_SINGLE, 20240 + args.config * 100, loop_frac=0.08, sigma=500.0)
-    frac = float(os.environ.get("CLOOPS_REF_FRAC", "0.03"))
+    frac = float(os.environ.get("CLOOPS_REF_FRAC", "0.03" if cfg["kind"] == "single" else "0.001"))
     m = X < int(CHROM_LEN_SINGLE * frac)
-    return [("chr1", X[m].astype(np.int64), Y[m].astype(np.int64))], "per step: the PETs with X < %.0f%% of the chromosome (same density)" % (frac * 100)
+    return [("chr1", X[m].astype(np.int64), Y[m].astype(np.int64))], "per step: the PETs with X < %.1f%% of the chromosome (same density)" % (frac * 100)
 
 
 class ReferenceRun:
@@ -251,9 +251,35 @@ class PortRun:
         pass
 
 
+class SweepReferenceRun:
+    """Config 5 on the CPU: the reference's cDBSCAN2 class on the sample at the four corner (eps, minPts) pairs of the grid
+    (BASELINE.md section 3); PETs/s counts one PET per pair, like the GPU arm."""
+
+    def __init__(self, cfg, sample, cores):
+        from oracle import ref_shim
+        self.ns = ref_shim.load()
+        name, X, Y = sample[0]
+        self.mat = np.stack([np.arange(len(X)), X, Y], axis=1).astype(np.int64)
+        self.pairs = [(cfg["eps"][0], min(cfg["minPts"])), (cfg["eps"][0], max(cfg["minPts"])),
+                      (cfg["eps"][-1], min(cfg["minPts"])), (cfg["eps"][-1], max(cfg["minPts"]))]
+        self.pets = len(X) * len(self.pairs)
+        self.cores = 1
+        self.kind = "reference-shim (%s), cDBSCAN2 at the 4 corner pairs %s" % (ref_shim.REF_ROOT, self.pairs)
+
+    def step(self):
+        for ep, m in self.pairs:
+            self.ns.cDBSCAN2(self.mat, ep, m)
+        return 0
+
+    def close(self):
+        pass
+
+
 def make_cpu_run(cfg, sample, cores):
     from oracle import ref_shim
-    return ReferenceRun(cfg, sample, cores) if ref_shim.available() else PortRun(cfg, sample, cores)
+    if not ref_shim.available():
+        return PortRun(cfg, sample, cores)
+    return SweepReferenceRun(cfg, sample, cores) if cfg["kind"] == "sweep" else ReferenceRun(cfg, sample, cores)
 
 
 def workload_config(cfg, args, world):
@@ -287,11 +313,12 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "PETs/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-        "scaling": "weak" if cfg["kind"] == "single" else "strong", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "scaling": "strong" if cfg["kind"] == "genome" else "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
         "config": workload_config(cfg, args, max(1, args.gpus)),
         "cpu_baseline": {"value": value, "unit": "PETs/s", "cores": used, "kind": run.kind,
-                         "sample": "%s: %d PETs, all %d rounds + scoring; PETs/s of the sample stands for the full workload (the reference's per-PET "
-                                   "cost grows with chromosome size, so this favours the reference)" % (what, run.pets, len(cfg["eps"]) * len(cfg["minPts"]))},
+                         "sample": "%s: %d PET-clusterings per step (%s); PETs/s of the sample stands for the full workload (the reference's per-PET "
+                                   "cost grows with chromosome size, so this favours the reference)" %
+                                   (what, run.pets, "clustering only, 4 corner (eps, minPts) pairs" if cfg["kind"] == "sweep" else "all %d rounds + scoring" % (len(cfg["eps"]) * len(cfg["minPts"])))},
         "e2e": {"value": value, "unit": "PETs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "result": {"loops_in_sample": loops},
     }
