@@ -559,7 +559,7 @@ def main():
         dt = time.perf_counter() - t0
         run.close()
         line["cpu_baseline"] = {"value": run.pets / dt, "unit": "PETs/s", "cores": min(run.cores, len(sample)), "kind": run.kind,
-                                "sample": "%s: %d PETs, all rounds + scoring, %.1f s" % (what, run.pets, dt)}
+                                "sample": "%s: %d PET-clusterings (%s), %.1f s" % (what, run.pets, "clustering only, 4 corner (eps, minPts) pairs" if cfg["kind"] == "sweep" else "all rounds + scoring", dt)}
     print(json.dumps(line), flush=True)
     dist.shutdown()
 

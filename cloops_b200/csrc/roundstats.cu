@@ -88,29 +88,64 @@ __global__ void __launch_bounds__(32 * RS_NQ) dist_stats_commit_kernel(const dou
     if (threadIdx.x == 0) atomicAdd(&mom[8], 1.0);
 }
 
-// the two middle order statistics of the histogrammed values: out[0] = value of rank (k-1)/2, out[1] = value of rank k/2
-// (0-based), k = mom[3]; -1 when k == 0, RS_BINS when the rank lies in the overflow bin
-__global__ void __launch_bounds__(1024) hist_middle_kernel(const int* __restrict__ hist, const double* __restrict__ mom, long long* __restrict__ out) {
-    __shared__ long long s_sum[1024];
-    const int per = (RS_BINS + 1 + 1023) / 1024;
-    const int b0 = threadIdx.x * per, b1 = min(b0 + per, RS_BINS + 1);
-    long long mine = 0;
-    for (int b = b0; b < b1; ++b) mine += hist[b];
-    s_sum[threadIdx.x] = mine;
+// The two middle order statistics of the histogrammed values: out[0] = value of rank (k-1)/2, out[1] = value of rank k/2
+// (0-based), k = mom[3]; -1 when k == 0, RS_BINS when the rank lies in the overflow bin.  Two launches: sums of 1024-bin
+// chunks (coalesced), then one CTA scans the chunk sums, finds the chunk of each rank and scans that chunk.
+#define RS_CHUNK 1024
+#define RS_NCHUNK ((RS_BINS + 1 + RS_CHUNK - 1) / RS_CHUNK)
+__global__ void __launch_bounds__(256) hist_chunk_kernel(const int* __restrict__ hist, long long* __restrict__ chunk) {
+    __shared__ long long s_w[8];
+    long long v = 0;
+    for (int t = threadIdx.x; t < RS_CHUNK; t += 256) {
+        const int b = blockIdx.x * RS_CHUNK + t;
+        if (b <= RS_BINS) v += hist[b];
+    }
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
     __syncthreads();
+    if (threadIdx.x == 0) {
+        long long tot = 0;
+        for (int w = 0; w < 8; ++w) tot += s_w[w];
+        chunk[blockIdx.x] = tot;
+    }
+}
+
+__global__ void __launch_bounds__(1024) hist_middle_kernel(const int* __restrict__ hist, const long long* __restrict__ chunk,
+                                                           const double* __restrict__ mom, long long* __restrict__ out) {
+    __shared__ long long s_before[RS_NCHUNK + 1];
+    __shared__ int s_bins[RS_CHUNK];
     const long long k = (long long)mom[3];
-    if (threadIdx.x == 0 && k == 0) { out[0] = -1; out[1] = -1; }
-    if (k == 0) return;
-    long long before = 0;
-    for (int t = 0; t < (int)threadIdx.x; ++t) before += s_sum[t];
+    if (k == 0) {
+        if (threadIdx.x == 0) { out[0] = -1; out[1] = -1; }
+        return;
+    }
+    if (threadIdx.x == 0) {                                  // 1025 chunk sums: a serial prefix is a microsecond
+        long long acc = 0;
+        for (int c = 0; c < RS_NCHUNK; ++c) { s_before[c] = acc; acc += chunk[c]; }
+        s_before[RS_NCHUNK] = acc;
+    }
+    __syncthreads();
     for (int w = 0; w < 2; ++w) {
         const long long r = w == 0 ? (k - 1) / 2 : k / 2;
-        if (r < before || r >= before + mine) continue;
-        long long acc = before;
-        for (int b = b0; b < b1; ++b) {
-            acc += hist[b];
-            if (r < acc) { out[w] = b; break; }
+        int c = 0;                                           // chunk holding rank r (every thread finds it: uniform)
+        for (int lo = 0, hi = RS_NCHUNK; lo < hi;) {
+            const int mid = (lo + hi) >> 1;
+            if (s_before[mid + 1] <= r) lo = mid + 1; else hi = mid;
+            c = lo;
         }
+        const int b = c * RS_CHUNK + threadIdx.x;
+        s_bins[threadIdx.x] = b <= RS_BINS ? hist[b] : 0;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            long long acc = s_before[c];
+            long long val = RS_BINS;
+            for (int t = 0; t < RS_CHUNK; ++t) {
+                acc += s_bins[t];
+                if (r < acc) { val = (long long)c * RS_CHUNK + t; break; }
+            }
+            out[w] = val;
+        }
+        __syncthreads();
     }
 }
 
@@ -137,9 +172,11 @@ extern "C" int cloops_round_middle(const int32_t* d_hist, const double* d_mom, i
     if (!d_hist || !d_mom || !h_middle || !h_mom) return fail(CLOOPS_EINVAL, "NULL argument");
     RET_IF(pool_init());
     Temp tmp(st);
-    long long* d_out;
+    long long *d_out, *d_chunk;
     RET_IF(tmp.alloc(&d_out, 2));
-    LAUNCH(hist_middle_kernel, 1, 1024, 0, st, d_hist, d_mom, d_out);
+    RET_IF(tmp.alloc(&d_chunk, RS_NCHUNK));
+    LAUNCH(hist_chunk_kernel, RS_NCHUNK, 256, 0, st, d_hist, d_chunk);
+    LAUNCH(hist_middle_kernel, 1, 1024, 0, st, d_hist, d_chunk, d_mom, d_out);
     long long out[2];
     CU_TRY(cudaMemcpyAsync(out, d_out, sizeof(out), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaMemcpyAsync(h_mom, d_mom, CLOOPS_ROUND_MOM * sizeof(double), cudaMemcpyDeviceToHost, st));
