@@ -51,6 +51,7 @@ _SIGNATURES = {
     "cloops_combine_rounds": (C.c_int, [_vp, _vp, _i64, _vp]),
     "cloops_pass_run": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, C.POINTER(_vp), _vp]),
     "cloops_pass_run_stats": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, C.POINTER(_vp), _vp]),
+    "cloops_pass_run_base": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, C.POINTER(_vp), _vp]),
     "cloops_round_middle": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "cloops_pass_run_host": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, C.POINTER(_vp), _vp]),
     "cloops_pass_sizes": (C.c_int, [_vp, _vp, _vp]),

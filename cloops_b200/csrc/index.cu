@@ -523,6 +523,105 @@ int index_build(const int32_t* d_x, const int32_t* d_y, int64_t n, int32_t eps, 
     return 0;
 }
 
+// ---- index of a cut-filtered round derived from the full (cut = 0) index of the same chromosome and eps -----------------
+// The (strip, u', row) order does not depend on the cut: the rows a round keeps (Y - X >= cut, cLoops/pipe.py:59-63) are a
+// subsequence of the full index, and Y - X = -u is in the key.  One stable compaction (tile counts, scan, copy) replaces
+// extents + pack + radix sort; the -m 3 / -m 4 presets cluster every eps with 2-4 minPts values, each with another cut.
+__global__ void __launch_bounds__(256) filter_count_kernel(const u64* __restrict__ keys, GridParams P, int n_in, int cut,
+                                                           int* __restrict__ blockcnt) {
+    const int i0 = blockIdx.x * EX_ROWS + 4 * threadIdx.x;
+    int c = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = i0 + k;
+        if (i < n_in) c += (-((int)((u32)((keys[i] & KEY_MASK) >> P.be) & P.umask) + P.ubase) >= cut) ? 1 : 0;
+    }
+    const int tot = __reduce_add_sync(0xffffffffu, c);
+    __shared__ int s_w[8];
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = tot;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < 8; ++w) t += s_w[w];
+        blockcnt[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256) filter_compact_kernel(const u64* __restrict__ keys_in, const u32* __restrict__ rows_in, GridParams P,
+                                                             int n_in, int cut, const int* __restrict__ blockbase,
+                                                             u64* __restrict__ keys_out, u32* __restrict__ rows_out) {
+    __shared__ int s_warp[8];
+    const int i0 = blockIdx.x * EX_ROWS + 4 * threadIdx.x;
+    u64 key[4];
+    unsigned act = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = i0 + k;
+        if (i >= n_in) continue;
+        key[k] = keys_in[i] & KEY_MASK;                      // a core flag of an earlier clustering of the full index is dropped
+        if (-((int)((u32)(key[k] >> P.be) & P.umask) + P.ubase) >= cut) act |= 1u << k;
+    }
+    const int mine = __popc(act), lane = threadIdx.x & 31;
+    int incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    if (lane == 31) s_warp[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    int pos = blockbase[blockIdx.x] + incl - mine;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) pos += s_warp[w];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (!(act & (1u << k))) continue;
+        keys_out[pos] = key[k];
+        rows_out[pos] = rows_in[i0 + k];
+        ++pos;
+    }
+}
+
+__global__ void filter_total_kernel(const int* __restrict__ blockbase, const int* __restrict__ blockcnt_last, int nblk, int* __restrict__ total) {
+    *total = blockbase[nblk - 1] + *blockcnt_last;
+}
+
+int index_filter(const cloops_index* base, int32_t cut, cloops_index** out, cudaStream_t st) {
+    if (!base) return fail(CLOOPS_EINVAL, "base index is NULL");
+    RET_IF(pool_init());
+    cloops_index* ix = new cloops_index();
+    *out = ix;
+    ix->P = base->P;
+    GridParams& P = ix->P;
+    const int n_in = base->P.n_act;
+    if (base->P.n == 0 || n_in == 0) { P.n_act = 0; return 0; }
+    if (cut <= 0) cut = INT_MIN;                             // no filter: every row of the full index stays (pipe.py:59 "if cut > 0")
+    Temp tmp(st);
+    const int nblk = cdiv(n_in, EX_ROWS);
+    int *d_cnt, *d_base, *d_total;
+    RET_IF(tmp.alloc(&d_cnt, nblk));
+    RET_IF(tmp.alloc(&d_base, nblk));
+    RET_IF(tmp.alloc(&d_total, 1));
+    LAUNCH(filter_count_kernel, nblk, 256, 0, st, base->keys, base->P, n_in, cut, d_cnt);
+    CU_TRY(cudaMemcpyAsync(d_base, d_cnt, (size_t)nblk * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    LAUNCH(blockcnt_scan_kernel, 1, 1024, 0, st, d_base, nblk);
+    LAUNCH(filter_total_kernel, 1, 1, 0, st, d_base, d_cnt + (nblk - 1), nblk, d_total);
+    int total = 0;
+    CU_TRY(cudaMemcpyAsync(&total, d_total, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    stage_mark("extents", st);
+    P.n_act = total;
+    if (total == 0) return 0;
+    CU_TRY(cudaMallocAsync((void**)&ix->keys, ((size_t)total + 2) * sizeof(u64), st));
+    CU_TRY(cudaMallocAsync((void**)&ix->rows, (size_t)total * sizeof(u32), st));
+    CU_TRY(cudaMallocAsync((void**)&ix->sstart, (size_t)(P.ns + 3) * sizeof(int), st));
+    LAUNCH(filter_compact_kernel, nblk, 256, 0, st, base->keys, base->rows, base->P, n_in, cut, d_base, ix->keys, ix->rows);
+    stage_mark("pack", st);
+    LAUNCH(strip_table_search_kernel, cdiv(P.ns + 3, 256), 256, 0, st, ix->keys, P, ix->sstart);
+    RET_IF(index_tiles(ix, st));
+    stage_mark("strips", st);
+    return 0;
+}
+
 void index_free(cloops_index* ix, cudaStream_t st) {
     if (!ix) return;
     if (ix->keys) cudaFreeAsync(ix->keys, st);

@@ -95,6 +95,7 @@ __device__ __forceinline__ void for_each_neighbour(const u64* __restrict__ keys,
 
 int index_build(const int32_t* d_x, const int32_t* d_y, int64_t n, int32_t eps, int32_t cut, cloops_index** out,
                 cudaStream_t st);
+int index_filter(const cloops_index* base, int32_t cut, cloops_index** out, cudaStream_t st);
 void index_free(cloops_index* ix, cudaStream_t st);
 int index_count(cloops_index* ix, int cap, int* d_counts_sorted, cudaStream_t st);   // region_query.cu
 int index_tiles(cloops_index* ix, cudaStream_t st);                                    // region_query.cu

@@ -103,7 +103,8 @@ static void pass_release(cloops_pass* p, cudaStream_t st) {
 }
 
 static int pass_run(cloops_pass* p, const int32_t* d_x, const int32_t* d_y, int64_t n, int32_t eps, int32_t minPts, int32_t cut,
-                    int32_t variant, int32_t score, cudaStream_t st, int32_t* d_hist = nullptr, double* d_mom = nullptr) {
+                    int32_t variant, int32_t score, cudaStream_t st, int32_t* d_hist = nullptr, double* d_mom = nullptr,
+                    const cloops_index* base = nullptr) {
     // every failure inside leaves through the common clean-up at the bottom (index, coverage model, join with the side stream)
 #define CU_BRK(expr)                                                                                                    \
     {                                                                                                                   \
@@ -136,7 +137,7 @@ static int pass_run(cloops_pass* p, const int32_t* d_x, const int32_t* d_y, int6
             if ((rc = dalloc(&p->labels, n, st))) break;
             if ((rc = block_dbscan(d_x, d_y, n, eps, minPts, cut, p->labels, p->info, st))) break;
         } else {
-            if ((rc = index_build(d_x, d_y, n, eps, cut, &ix, st))) break;
+            if ((rc = base ? index_filter(base, cut, &ix, st) : index_build(d_x, d_y, n, eps, cut, &ix, st))) break;
             p->n_members = ix->P.n_act;
             if ((rc = dalloc(&p->labels, p->n_members, st))) break;
             if ((rc = index_dbscan(ix, minPts, variant, nullptr, p->labels, p->info, st))) break;
@@ -222,6 +223,27 @@ int cloops_pass_run_stats(const int32_t* d_x, const int32_t* d_y, int64_t n, int
     stages_begin(st);
     cloops_pass* p = new cloops_pass();
     int rc = pass_run(p, d_x, d_y, n, eps, minPts, cut, variant, score, st, d_hist, d_mom);
+    if (rc != 0) {
+        pass_release(p, st);
+        return rc;
+    }
+    *out = p;
+    return stages_end(st);
+}
+
+int cloops_pass_run_base(const cloops_index* base, const int32_t* d_x, const int32_t* d_y, int64_t n, int32_t minPts, int32_t cut,
+                         int32_t variant, int32_t score, int32_t* d_hist, double* d_mom, cloops_pass** out, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!out) return fail(CLOOPS_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (!base) return fail(CLOOPS_EINVAL, "base index is NULL");
+    if (n != base->P.n) return fail(CLOOPS_EINVAL, "the base index was built for %d rows, not %lld", base->P.n, (long long)n);
+    if (minPts < 1) return fail(CLOOPS_EINVAL, "minPts must be >= 1 (got %d)", minPts);
+    if (variant != CLOOPS_V1 && variant != CLOOPS_V2) return fail(CLOOPS_EINVAL, "variant %d has no strip index", variant);
+    if ((d_hist == nullptr) != (d_mom == nullptr)) return fail(CLOOPS_EINVAL, "round accumulators: both or none");
+    stages_begin(st);
+    cloops_pass* p = new cloops_pass();
+    int rc = pass_run(p, d_x, d_y, n, base->P.eps, minPts, cut, variant, score, st, d_hist, d_mom, base);
     if (rc != 0) {
         pass_release(p, st);
         return rc;

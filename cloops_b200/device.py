@@ -147,11 +147,14 @@ class Index:
 
     def __init__(self, dx: torch.Tensor, dy: torch.Tensor, eps: int, cut: int = 0):
         self.n = dx.numel()
+        self.eps = int(eps)
         self._dx, self._dy = dx, dy           # keep inputs alive
         h = C.c_void_p()
         check(_lib.lib().cloops_index_build(dx.data_ptr(), dy.data_ptr(), self.n, int(eps), int(cut), C.byref(h), _stream()))
         self._h = h
         self.n_active = int(_lib.lib().cloops_index_n_active(h))
+        if Profile.on:
+            Profile.add_stages()
 
     def count(self, cap: int, out: torch.Tensor | None = None) -> torch.Tensor:
         if out is None:
@@ -262,7 +265,7 @@ class Pass:
               "labels_sorted": (5, "<i4"), "member_kind": (6, "|u1"), "cand": (7, "<i4"), "counts": (8, "<i4")}
 
     def __init__(self, x, y, eps: int, minPts: int, variant: int = _lib.V2, cut: int = 0, score: bool = True, host: bool = False,
-                 stats=None):
+                 stats=None, base: "Index | None" = None):
         """``stats`` = (hist int32 CUDA tensor [ROUND_HIST_BINS + 1], mom float64 CUDA tensor [ROUND_MOM]): the round's distance
         accumulators this chromosome adds to (cloops_pass_run_stats)."""
         require_cuda()
@@ -270,7 +273,15 @@ class Pass:
         n = x.numel()
         h = C.c_void_p()
         args = (x.data_ptr(), y.data_ptr(), n, int(eps), int(minPts), int(cut), int(variant), 1 if score else 0)
-        if stats is not None:
+        if base is not None:
+            # ``base``: the chromosome's index for this eps built with cut = 0; the round's index is a compaction of it
+            if host or base.eps != int(eps):
+                raise CloopsError("the base index must be device-resident and built for the same eps")
+            self._keep += (base,)
+            check(_lib.lib().cloops_pass_run_base(base._h, x.data_ptr(), y.data_ptr(), n, int(minPts), int(cut), int(variant), 1 if score else 0,
+                                                  stats[0].data_ptr() if stats is not None else None,
+                                                  stats[1].data_ptr() if stats is not None else None, C.byref(h), _stream()))
+        elif stats is not None:
             if host:
                 raise CloopsError("round statistics need device-resident coordinates")
             check(_lib.lib().cloops_pass_run_stats(*args, stats[0].data_ptr(), stats[1].data_ptr(), C.byref(h), _stream()))

@@ -54,6 +54,21 @@ class _Resident:
         self.n = len(X)
         self.dx = device.to_device_i32(X, "X") if dx is None else dx
         self.dy = device.to_device_i32(Y, "Y") if dy is None else dy
+        self._base = None                  # (eps, device.Index built with cut = 0): shared by the rounds of one eps
+
+    def base_index(self, eps):
+        """The chromosome's full (cut = 0) index for ``eps``, built on first use and kept until another eps is asked for."""
+        if self._base is not None and self._base[0] != eps:
+            self._base[1].close()
+            self._base = None
+        if self._base is None:
+            self._base = (eps, device.Index(self.dx, self.dy, int(eps), 0))
+        return self._base[1]
+
+    def drop_base(self):
+        if self._base is not None:
+            self._base[1].close()
+            self._base = None
 
     @classmethod
     def get(cls, f):
@@ -93,6 +108,8 @@ class _Resident:
 
     @classmethod
     def clear(cls):
+        for _, ch in cls._cache.values():
+            ch.drop_base()
         cls._cache.clear()
 
 
@@ -170,6 +187,11 @@ class _RoundAcc:
         return int(mid[0]), int(mid[1]), [float(v) for v in mom]
 
 
+#: set per run by _rounds: an eps clustered with several minPts values (presets -m 3 / -m 4) builds the chromosome's index once
+#: (cut = 0) and derives every round's index from it by a compaction instead of a sort (cloops_pass_run_base)
+REUSE_INDEX = False
+
+
 def _weights(fs):
     """PETs per chromosome file (LPT packing of chromosomes onto ranks, dist.assign): a .jd holds 24 B per PET."""
     out = []
@@ -190,8 +212,9 @@ def _cluster_chrom(f, eps, minPts, cut, acc):
         return key, empty, 0
     sys.stderr.write("Clustering %s and %s using eps as %s, minPts as %s,pre-set distance cutoff as > %s\n" %
                      (key[0], key[1], eps, minPts, cut))
+    base = ch.base_index(int(eps)) if (REUSE_INDEX and DBSCAN_VARIANT != _lib.BLOCK) else None
     p = device.Pass(ch.dx, ch.dy, int(eps), int(minPts), DBSCAN_VARIANT, int(cut) if cut > 0 else 0, score=False,
-                    stats=(acc.hist, acc.mom))
+                    stats=(acc.hist, acc.mom), base=base)
     bbox, size, kind = p.records()
     p.close()
     sys.stderr.write("Clustering %s and %s finished. Estimated %s self-ligation reads and %s inter-ligation reads\n" %
@@ -297,6 +320,8 @@ def _rounds(cfs, eps, minPts, cut, max_cut, log, weights=None, finalize=True):
     """The round loop of cLoops/pipe.py:247-281: clustering rounds with the distance cut-off fed forward, candidates of all
     rounds merged (combineTwice) and filtered by the final cut-off.  -> (dataI of this rank's chromosomes with records as
     int64 arrays [K,4] and "first" = first round that produced the chromosome, final cut)"""
+    global REUSE_INDEX
+    REUSE_INDEX = len(minPts) > 1 and os.environ.get("CLOOPS_REUSE_INDEX", "1") != "0"
     dataI, cuts, rnd = {}, [cut], 0
     for ep in eps:
         for m in minPts:
@@ -312,6 +337,8 @@ def _rounds(cfs, eps, minPts, cut, max_cut, log, weights=None, finalize=True):
             log.info("Estimated inter-ligation and self-ligation distance cutoff as %s for eps=%s,minPts=%s" % (cut_2, ep, m))
             cuts.append(cut_2)
             cut = cut_2
+    for hit in _Resident._cache.values():                      # the per-eps base indexes are not needed for scoring
+        hit[1].drop_base()
     cuts = [c for c in cuts if c > 0]
     cut = np.max(cuts) if max_cut else np.min(cuts)
     if finalize:

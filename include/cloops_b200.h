@@ -145,6 +145,12 @@ CLOOPS_API int cloops_pass_run(const int32_t* d_x, const int32_t* d_y, int64_t n
 #define CLOOPS_ROUND_MOM 16
 CLOOPS_API int cloops_pass_run_stats(const int32_t* d_x, const int32_t* d_y, int64_t n, int32_t eps, int32_t minPts, int32_t cut,
                           int32_t variant, int32_t score, int32_t* d_hist, double* d_mom, cloops_pass** out, void* stream);
+/* The same pass for a round that shares eps with earlier rounds: `base` is the index of the chromosome built ONCE for this eps
+ * with cut = 0 (cloops_index_build); the rows this round keeps (Y - X >= cut, cLoops/pipe.py:59-63) are a subsequence of it, so
+ * the round's index is one stable compaction of the base instead of a sort.  d_hist / d_mom may both be NULL.  The presets
+ * -m 3 / -m 4 (cLoops/pipe.py:337-344) cluster every eps with 2-4 minPts values, each with the cut of the round before. */
+CLOOPS_API int cloops_pass_run_base(const cloops_index* base, const int32_t* d_x, const int32_t* d_y, int64_t n, int32_t minPts,
+                         int32_t cut, int32_t variant, int32_t score, int32_t* d_hist, double* d_mom, cloops_pass** out, void* stream);
 /* The two middle order statistics of the histogram (ranks (k-1)/2 and k/2 of the k = d_mom[3] positive self-ligation
  * distances; -1 if k = 0, CLOOPS_ROUND_HIST_BINS if a rank lies in the overflow bin) and a host copy of d_mom: what
  * estIntSelCutFrag (cLoops/ests.py:36-61) needs.  Synchronises the stream. */
