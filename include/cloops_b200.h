@@ -15,6 +15,13 @@
  *                            dis/dss membership)
  *   cloops_range_counts      cLoops/cModel.py:60-143 (getCounts / getPETsforRegions /
  *                            getNearbyPairRegions / the counting half of getMultiplePsFdr)
+ *   cloops_pass_run*         cLoops/pipe.py:52-110 singleDBSCAN for one chromosome and round (cut filter, clusterer, records,
+ *                            dis / dss membership) [+ cModel.py:262-295 getIntSig's counting half with score = 1]
+ *   cloops_pass_run_stats / _base, cloops_round_middle
+ *                            the pooled dis / dss lists of cLoops/pipe.py:113-127 and their reduction by
+ *                            cLoops/ests.py:36-61 estIntSelCutFrag (mean / std / median of log2 distances)
+ *   cloops_combine_rounds    cLoops/pipe.py:155-174 combineTwice (host C++)
+ *   cloops_remove_dup        cLoops/cModel.py:198-259 removeDup (host C++)
  */
 #ifndef CLOOPS_B200_H
 #define CLOOPS_B200_H
