@@ -339,9 +339,9 @@ def main():
     cfg = CONFIGS[args.config]
     if args.pets <= 0:
         args.pets = cfg["pets"]
+    args.warmup = max(args.warmup, 3)                      # both arms: at least three untimed steps, the same K timed ones
     if args.impl == "reference":
         return run_reference(args)
-    args.warmup = max(args.warmup, 3)
 
     import torch
     from cloops_b200 import _lib, device, dist, pipe, synth
