@@ -79,3 +79,32 @@ def test_rounds_match_oracle_pipeline(eps_list, mp_list, dens, monkeypatch):
     assert sorted(k[0] for k in run["dataI"]) == sorted(want)
     for key, v in run["dataI"].items():
         assert np.array_equal(np.asarray(v["records"], np.int64), want[key[0]]), key
+
+
+@pytest.mark.parametrize("variant", [2, 1])
+def test_pass_from_full_index_equals_fresh_build(variant):
+    """cloops_pass_run_base (the round's index as a compaction of the chromosome's cut = 0 index) must give exactly what
+    cloops_pass_run_stats gives with a freshly built index: labels in index order, coordinates, records, the round
+    statistics -- for no cut, ordinary cuts, a cut that removes every row, and negative / mixed coordinates."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from cloops_b200 import _lib, device, synth
+    X, Y = synth.chromosome(250_000, 4_000_000, seed=77, loop_frac=0.15, sigma=600.0)
+    sets = [(X, Y), (X - 1_500_000, Y - 1_500_000)]
+    for X, Y in sets:
+        dx, dy = device.to_device_i32(X), device.to_device_i32(Y)
+        for eps, mp in ((1500, 6), (6000, 25)):
+            base = device.Index(dx, dy, eps, 0)
+            for cut in (0, 900, 7000, 40_000_000):
+                out = []
+                for use_base in (False, True):
+                    hist = torch.zeros(_lib.ROUND_HIST_BINS + 1, dtype=torch.int32, device="cuda")
+                    mom = torch.zeros(_lib.ROUND_MOM, dtype=torch.float64, device="cuda")
+                    p = device.Pass(dx, dy, eps, mp, variant, cut, score=False, stats=(hist, mom), base=base if use_base else None)
+                    bbox, size, kind = p.records()
+                    out.append((p.n_members, p.info["n_clusters"], p.info["n_dead"], bbox, size, kind, p.xs.cpu().numpy(), p.ys.cpu().numpy(),
+                                p.labels_sorted.cpu().numpy(), hist.cpu().numpy(), mom.cpu().numpy()))
+                    p.close()
+                for a, b in zip(*out):
+                    assert np.array_equal(a, b), (eps, mp, cut)
+            base.close()
