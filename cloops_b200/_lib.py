@@ -49,6 +49,15 @@ _SIGNATURES = {
     "cloops_region_pets": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "cloops_remove_dup": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, C.c_double, _vp, _vp, _vp, _vp, _vp]),
     "cloops_combine_rounds": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "cloops_bedpe_parse": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _i64, C.c_int, C.POINTER(_vp)]),
+    "cloops_bedpe_lines": (_i64, [_vp]),
+    "cloops_bedpe_bare_cr": (_i64, [_vp]),
+    "cloops_bedpe_n_chroms": (C.c_int, [_vp]),
+    "cloops_bedpe_chrom": (_vp, [_vp, C.c_int, _vp, _vp]),
+    "cloops_bedpe_fetch": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp]),
+    "cloops_bedpe_n_odd": (_i64, [_vp]),
+    "cloops_bedpe_odd": (_vp, [_vp, _i64, _vp, _vp]),
+    "cloops_bedpe_free": (None, [_vp]),
     "cloops_pass_run": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, C.POINTER(_vp), _vp]),
     "cloops_pass_run_stats": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, C.POINTER(_vp), _vp]),
     "cloops_pass_run_base": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, C.POINTER(_vp), _vp]),

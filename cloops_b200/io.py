@@ -1,13 +1,19 @@
 """File formats either side of the hot path (cLoops/io.py).  BEDPE ingest and the .jd container are
-boundary code: same observable behaviour as the reference, written for numpy instead of per-line
-Python objects.  Converters that shell out to external tools (jd2washU, jd2hic) are out of scope."""
+boundary code: same observable behaviour as the reference.  The text is read by the native reader of
+libcloops_b200 (``cloops_bedpe_parse``: one inflate/read thread + a pool of tokenizers, csrc/ingest.cu);
+lines it does not decide (coordinates that are not plain decimal integers) go through the per-line PET class
+below, i.e. through the reference's own expression.  Converters that shell out to external tools (jd2washU,
+jd2hic) are out of scope."""
 from __future__ import annotations
 
+import ctypes as C
 import gzip
 import os
 
 import joblib
 import numpy as np
+
+from . import _lib
 
 
 class PET(object):
@@ -65,7 +71,7 @@ def _cis_pets(fs, cs, cut, logger, need_strand):
 def _write_jd(fout, chrom_arrays, order):
     cfs = []
     for c in order:
-        a, b = chrom_arrays[c]
+        a, b = chrom_arrays[c][:2]
         mat = np.empty((len(a), 3), dtype=np.int64)
         mat[:, 0] = np.arange(len(a))
         mat[:, 1] = a
@@ -162,43 +168,80 @@ class _NullLog:
         pass
 
 
-def _group_by_chrom(chrom, a, b):
-    """file order inside each chromosome, chromosomes in order of first appearance"""
-    import pandas as pd
-    codes, uniques = pd.factorize(chrom, sort=False)
-    out, order = {}, []
-    for k, name in enumerate(uniques.tolist()):
-        m = codes == k
-        out[name] = (a[m], b[m])
-        order.append(name)
-    return out, order
+INGEST_THREADS = 0          # 0: one tokenizer per host core
 
 
-def parseRawBedpe2(fs, fout, cs, cut, logger):
-    """cLoops/io.py:132-189 + txt2jd (:192-203) in one step: per-chromosome ``[id, cA, cB]`` int64
-    matrices (id restarts at 0 per chromosome, rows in file order) written straight to ``.jd``.
-    Returns the list of .jd paths in order of first appearance."""
-    parts, total = [], 0
+def _accept_odd(text, cs, cut):
+    """One line the native reader handed back: the reference's per-line decision (io.py:154-176)."""
+    t = text.split("\t")
+    if ("*" in t and "-1" in t) or len(t) < 6:
+        return None
+    try:
+        pet = PET(t)
+    except Exception:
+        return None
+    if pet.chromA != pet.chromB or (len(cs) > 0 and pet.chromA not in cs) or (cut > 0 and pet.distance < cut):
+        return None
+    return pet.chromA, pet.cA, pet.cB, pet.strandA != pet.strandB
+
+
+def _cis_native(fs, cs, cut):
+    """All files through ``cloops_bedpe_parse``.  -> (order, {chrom: (cA, cB, opposite, line_no)}, n_lines);
+    chromosomes in order of first appearance, PETs in file order (io.py:177-185).  None when a file holds a carriage
+    return outside "\\r\\n" (python's text mode would split the line there): the caller reads such input line by line."""
+    L = _lib.lib()
+    paths = (C.c_char_p * max(len(fs), 1))(*[os.fsencode(f) for f in fs])
+    names = sorted(cs)
+    wanted = (C.c_char_p * max(len(names), 1))(*[c.encode() for c in names])
+    h = C.c_void_p()
+    _lib.check(L.cloops_bedpe_parse(paths, len(fs), wanted, len(names), int(cut), INGEST_THREADS, C.byref(h)))
+    try:
+        if L.cloops_bedpe_bare_cr(h) > 0:
+            return None
+        order, per = [], {}
+        ln, npets, where = C.c_int64(), C.c_int64(), C.c_int64()
+        for k in range(L.cloops_bedpe_n_chroms(h)):
+            ptr = L.cloops_bedpe_chrom(h, k, C.byref(ln), C.byref(npets))
+            name = C.string_at(ptr, ln.value).decode()
+            a = np.empty(npets.value, np.int64)
+            b = np.empty(npets.value, np.int64)
+            opp = np.empty(npets.value, np.uint8)
+            line = np.empty(npets.value, np.int64)
+            _lib.check(L.cloops_bedpe_fetch(h, k, a.ctypes.data, b.ctypes.data, opp.ctypes.data, line.ctypes.data))
+            order.append(name)
+            per[name] = (a, b, opp.view(bool), line)
+        extra = {}
+        for k in range(L.cloops_bedpe_n_odd(h)):
+            ptr = L.cloops_bedpe_odd(h, k, C.byref(where), C.byref(ln))
+            got = _accept_odd(C.string_at(ptr, ln.value).decode(), cs, cut)
+            if got is not None:
+                extra.setdefault(got[0], []).append((where.value,) + got[1:])
+        if extra:                                   # merge by line number; chromosome order = first accepted line
+            none = (np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, bool), np.zeros(0, np.int64))
+            for name, rows in extra.items():
+                a, b, opp, line = per.get(name, none)
+                line = np.concatenate([line, np.array([r[0] for r in rows], np.int64)])
+                a = np.concatenate([a, np.array([r[1] for r in rows], np.int64)])
+                b = np.concatenate([b, np.array([r[2] for r in rows], np.int64)])
+                opp = np.concatenate([opp, np.array([r[3] for r in rows], bool)])
+                o = np.argsort(line, kind="stable")
+                per[name] = (a[o], b[o], opp[o], line[o])
+            order = sorted(per, key=lambda c: per[c][3][0])
+        return order, per, int(L.cloops_bedpe_lines(h))
+    finally:
+        L.cloops_bedpe_free(h)
+
+
+def _cis_all(fs, cs, cut, logger):
+    """-> (order, {chrom: (cA, cB, opposite, seq)}, n_lines) over all files, seq increasing in file order: the native
+    reader, or -- for input with bare carriage returns -- the tokenizer of pandas with the per-line class behind it."""
     for f in fs:
         logger.info("Parsing PETs from %s, requiring initial distance cutoff > %s" % (f, cut))
-        chrom, a, b, _, n = _cis_table(f, cs, cut)
-        parts.append((chrom, a, b))
-        total += n
-    chrom = np.concatenate([p[0] for p in parts]) if parts else np.zeros(0, dtype=object)
-    a = np.concatenate([p[1] for p in parts]) if parts else np.zeros(0, np.int64)
-    b = np.concatenate([p[2] for p in parts]) if parts else np.zeros(0, np.int64)
-    logger.info("Totaly %s PETs from %s, in which %s cis PETs" % (total, ",".join(fs), len(a)))
-    per, order = _group_by_chrom(chrom, a, b)
-    return _write_jd(fout, per, order)
-
-
-def parseRawBedpe(fs, fout, cs, cut, logger):
-    """cLoops/io.py:62-129: as parseRawBedpe2 but drops duplicate (cA, cB) per chromosome (first one
-    wins) and collects the distances of opposite-strand PETs (input of estFragSize when eps is auto)."""
-    import pandas as pd
+    got = _cis_native(fs, cs, cut)
+    if got is not None:
+        return got
     parts, total = [], 0
     for f in fs:
-        logger.info("Parsing PETs from %s, requiring initial distance cutoff > %s" % (f, cut))
         chrom, a, b, opp, n = _cis_table(f, cs, cut)
         parts.append((chrom, a, b, opp))
         total += n
@@ -206,11 +249,56 @@ def parseRawBedpe(fs, fout, cs, cut, logger):
     a = np.concatenate([p[1] for p in parts]) if parts else np.zeros(0, np.int64)
     b = np.concatenate([p[2] for p in parts]) if parts else np.zeros(0, np.int64)
     opp = np.concatenate([p[3] for p in parts]) if parts else np.zeros(0, bool)
-    first = ~pd.DataFrame({"c": chrom, "a": a, "b": b}).duplicated(keep="first").to_numpy() if len(a) else np.zeros(0, bool)
-    chrom, a, b, opp = chrom[first], a[first], b[first], opp[first]
-    logger.info("Totaly %s PETs from %s, in which %s cis PETs" % (total, ",".join(fs), len(a)))
-    per, order = _group_by_chrom(chrom, a, b)
-    return _write_jd(fout, per, order), (b - a)[opp].tolist()
+    seq = np.arange(len(a), dtype=np.int64)
+    import pandas as pd
+    codes, uniques = pd.factorize(chrom, sort=False)
+    per, order = {}, []
+    for k, name in enumerate(uniques.tolist()):
+        m = codes == k
+        per[name] = (a[m], b[m], opp[m], seq[m])
+        order.append(name)
+    return order, per, total
+
+
+def readBedpe(fs, cs, cut, logger, dedup=False):
+    """The PETs parseRawBedpe2 (dedup False, cLoops/io.py:132-189) or parseRawBedpe (dedup True, :62-129) would write, kept
+    in memory: -> (order, {chrom: (cA, cB)}, ds).  ``order``: chromosomes by first appearance; cA, cB int64 in file order
+    (the row id of the reference's text file is the position); ``ds``: with dedup, the distances of the kept PETs whose
+    strands differ, in file order over all chromosomes (:126-127), else None.  dedup drops a PET whose (cA, cB) was seen
+    before on its chromosome (:114-115)."""
+    order, per, total = _cis_all(fs, cs, cut, logger)
+    kept, ds, seqs = {}, [], []
+    for c in order:
+        a, b, opp, seq = per[c]
+        if dedup:
+            import pandas as pd
+            first = ~pd.DataFrame({"a": a, "b": b}).duplicated(keep="first").to_numpy() if len(a) else np.zeros(0, bool)
+            kept[c] = (a[first], b[first])
+            ds.append((b - a)[first & opp])
+            seqs.append(seq[first & opp])
+        else:
+            kept[c] = (a, b)
+    logger.info("Totaly %s PETs from %s, in which %s cis PETs" % (total, ",".join(fs), sum(len(kept[c][0]) for c in order)))
+    if not dedup:
+        return order, kept, None
+    if ds:
+        ds = np.concatenate(ds)[np.argsort(np.concatenate(seqs), kind="stable")].tolist()
+    return order, kept, ds
+
+
+def parseRawBedpe2(fs, fout, cs, cut, logger):
+    """cLoops/io.py:132-189 + txt2jd (:192-203) in one step: per-chromosome ``[id, cA, cB]`` int64
+    matrices (id restarts at 0 per chromosome, rows in file order) written straight to ``.jd``.
+    Returns the list of .jd paths in order of first appearance."""
+    order, per, _ = readBedpe(fs, cs, cut, logger)
+    return _write_jd(fout, per, order)
+
+
+def parseRawBedpe(fs, fout, cs, cut, logger):
+    """cLoops/io.py:62-129: as parseRawBedpe2 but drops duplicate (cA, cB) per chromosome (first one
+    wins) and collects the distances of opposite-strand PETs (input of estFragSize when eps is auto)."""
+    order, per, ds = readBedpe(fs, cs, cut, logger, dedup=True)
+    return _write_jd(fout, per, order), ds
 
 
 def txt2jd(f):

@@ -20,7 +20,7 @@ from . import _lib, device, dist
 from . import cModel
 from .cModel import getIntSig, markIntSig, markIntSigHic
 from .ests import cut_from_round, estFragSize, estIntSelCutFrag
-from .io import loops2juice, loops2washU, parseJd, parseRawBedpe, parseRawBedpe2
+from .io import loops2juice, loops2washU, parseJd, parseRawBedpe, parseRawBedpe2, readBedpe
 from .utils import getLogger, mainHelp
 
 logger = None
@@ -508,6 +508,10 @@ def _log():
     return logger
 
 
+#: one process that does not keep the temporary files (no ``-s``) skips the .jd round trip; CLOOPS_MEMORY_INGEST=0 writes them
+MEMORY_INGEST = os.environ.get("CLOOPS_MEMORY_INGEST", "1") != "0"
+
+
 def pipe(fs, fout, eps, minPts, chroms="", cpu=1, tmp=0, hic=0, washU=0, juice=0, cut=0, plot=0, max_cut=False):
     """cLoops/pipe.py:206-295."""
     log = _log()
@@ -523,14 +527,20 @@ def pipe(fs, fout, eps, minPts, chroms="", cpu=1, tmp=0, hic=0, washU=0, juice=0
             os.mkdir(fout)
     if not dist.broadcast_object(ok):
         return
-    if dist.rank() == 0:
-        if eps == 0:
-            cfs, ds = parseRawBedpe(fs, fout, chroms, cut, log)
-        else:
-            cfs, ds = parseRawBedpe2(fs, fout, chroms, cut, log), None
+    if dist.world() == 1 and not tmp and MEMORY_INGEST:
+        # the per-chromosome .jd files (pipe.py:231-236) only carry the PETs to the workers and are deleted at the end
+        # unless -s is given (pipe.py:293-294): one process that does not keep them goes from the text to HBM directly
+        order, per, ds = readBedpe(fs, chroms, cut, log, dedup=(eps == 0))
+        cfs = [_Resident.register(c, *per[c]) for c in order]
     else:
-        cfs, ds = None, None
-    cfs, ds = dist.broadcast_object((cfs, ds))
+        if dist.rank() == 0:
+            if eps == 0:
+                cfs, ds = parseRawBedpe(fs, fout, chroms, cut, log)
+            else:
+                cfs, ds = parseRawBedpe2(fs, fout, chroms, cut, log), None
+        else:
+            cfs, ds = None, None
+        cfs, ds = dist.broadcast_object((cfs, ds))
     if eps == 0:
         eps = [estFragSize(ds) * 2]
     log.info("Starting estimate significance for interactions using distance cutoff as 0")

@@ -22,6 +22,7 @@
  *                            cLoops/ests.py:36-61 estIntSelCutFrag (mean / std / median of log2 distances)
  *   cloops_combine_rounds    cLoops/pipe.py:155-174 combineTwice (host C++)
  *   cloops_remove_dup        cLoops/cModel.py:198-259 removeDup (host C++)
+ *   cloops_bedpe_*           cLoops/io.py:30-59,62-189,192-203 BEDPE ingest: PET, parseRawBedpe / parseRawBedpe2, txt2jd (host C++)
  */
 #ifndef CLOOPS_B200_H
 #define CLOOPS_B200_H
@@ -192,6 +193,28 @@ CLOOPS_API int cloops_remove_dup(const int64_t* a0, const int64_t* a1, const int
 /* combineTwice (cLoops/pipe.py:155-174) over all clustering rounds of one chromosome at once: rows int32[n,4] = candidate
  * boxes of every round in round order, round int32[n]; keep u8[n] = 0 iff the same box came from an EARLIER round.  Host C++. */
 CLOOPS_API int cloops_combine_rounds(const int32_t* rows, const int32_t* round, int64_t n, uint8_t* keep);
+
+/* ---- BEDPE ingest (cLoops/io.py:132-189 parseRawBedpe2 / :62-129 parseRawBedpe, with the PET arithmetic of :30-59 and the
+ * text -> matrix step of txt2jd :192-203): host C++, one reader thread (zlib for *.gz, io.py:148-151) + `threads` tokenizers.
+ * paths: the replicate files in command-line order; chroms: the wanted chromosomes (n_chroms = 0: all, io.py:171);
+ * cut: initial distance cut-off (io.py:174).  Per chromosome, in order of first appearance, the accepted cis PETs in file
+ * order: cA, cB int64 (floor centres, left <= right), opposite u8 (strandA != strandB, the PETs parseRawBedpe collects for
+ * estFragSize, io.py:126-127), line_no int64 (0-based over all files).  Lines whose coordinates python's int() may still
+ * accept but that are not plain decimal integers are NOT decided here: they are returned verbatim ("odd" lines) with their
+ * line number and the caller applies the reference's own expression; bare_cr counts lines holding a carriage return that
+ * is not part of "\r\n" (python 3 splits there, python 2 does not): callers re-read such files line by line. */
+typedef struct cloops_bedpe cloops_bedpe;
+CLOOPS_API int cloops_bedpe_parse(const char* const* paths, int n_paths, const char* const* chroms, int n_chroms, int64_t cut,
+                       int threads, cloops_bedpe** out);
+CLOOPS_API int64_t cloops_bedpe_lines(const cloops_bedpe* h);        /* lines read: the reference's counter i (io.py:153) */
+CLOOPS_API int64_t cloops_bedpe_bare_cr(const cloops_bedpe* h);
+CLOOPS_API int cloops_bedpe_n_chroms(const cloops_bedpe* h);
+/* name (not NUL-terminated beyond name_len bytes of payload) and PET count of chromosome k */
+CLOOPS_API const char* cloops_bedpe_chrom(const cloops_bedpe* h, int k, int64_t* name_len, int64_t* n_pets);
+CLOOPS_API int cloops_bedpe_fetch(const cloops_bedpe* h, int k, int64_t* cA, int64_t* cB, uint8_t* opposite, int64_t* line_no);
+CLOOPS_API int64_t cloops_bedpe_n_odd(const cloops_bedpe* h);
+CLOOPS_API const char* cloops_bedpe_odd(const cloops_bedpe* h, int64_t k, int64_t* line_no, int64_t* len);
+CLOOPS_API void cloops_bedpe_free(cloops_bedpe* h);
 
 #ifdef __cplusplus
 }

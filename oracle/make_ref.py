@@ -1,5 +1,5 @@
 """Recipe for ``oracle/_ref/``: a byte-for-byte copy of the reference's Python package (and the four side scripts
-that call the hot path), made from ``/root/reference`` where it lies.  Test / measurement infrastructure only.
+that call the hot path), plus its bundled chr21 example file, made from ``/root/reference`` where it lies.  Test / measurement infrastructure only.
 
 ``oracle/_ref/`` is git-ignored (no reference source enters the history) but NOT gpurun-ignored, so the copy travels to
 the GPU box with the snapshot, where ``/root/reference`` does not exist.  ``oracle/ref_shim.py`` executes these UNMODIFIED
@@ -22,13 +22,14 @@ DST = os.path.join(HERE, "_ref")
 PACKAGE = ["__init__.py", "cDBSCAN.py", "cDBSCAN2.py", "blockDBSCAN.py", "cModel.py", "pipe.py", "io.py", "ests.py", "utils.py",
            "settings.py", "cPlots.py"]
 SCRIPTS = ["jd2saturation", "callStripes", "deLoops", "quantifyLoops.py"]
+EXAMPLES = ["GSM1872886_GM12878_CTCF_ChIA-PET_chr21_hg38.bedpe.gz"]      # the reference's only fixture: ingest parity
 
 
 def make(verbose: bool = False) -> bool:
     """-> True when oracle/_ref is complete (copied now or already there)."""
     if not os.path.isfile(os.path.join(SRC, "cLoops", "cDBSCAN2.py")):
         return os.path.isfile(os.path.join(DST, "cLoops", "cDBSCAN2.py"))
-    for sub, names in (("cLoops", PACKAGE), ("scripts", SCRIPTS)):
+    for sub, names in (("cLoops", PACKAGE), ("scripts", SCRIPTS), ("examples", EXAMPLES)):
         os.makedirs(os.path.join(DST, sub), exist_ok=True)
         for name in names:
             a, b = os.path.join(SRC, sub, name), os.path.join(DST, sub, name)

@@ -234,6 +234,135 @@ def test_columnar_ingest_equals_line_parser(tmp_path):
         assert n == len(lines)
 
 
+def _adversarial_lines(rng, n, crlf=False):
+    lines = []
+    for k in range(n):
+        c1 = "chr%d" % rng.integers(1, 5)
+        c2 = c1 if rng.random() < 0.8 else "chr%d" % rng.integers(1, 5)
+        a = int(rng.integers(0, 100000)); b = int(rng.integers(0, 100000))
+        t = [c1, str(a), str(a + int(rng.integers(0, 200))), c2, str(b), str(b + int(rng.integers(0, 200))), "n%d" % k, ".",
+             "+-"[rng.integers(0, 2)], "+-"[rng.integers(0, 2)]]
+        r = rng.random()
+        if r < 0.02: t = t[:int(rng.integers(1, 10))]            # short line
+        elif r < 0.04: t[1] = "x12"                               # not an int
+        elif r < 0.06: t[4] = " 77"                               # int() accepts it: an "odd" line, decided by the PET class
+        elif r < 0.08: t[2] = "+5"
+        elif r < 0.10: t = ["*", "-1", "-1", "*", "-1", "-1", "n", ".", "+", "-"]
+        elif r < 0.12: t += ["extra", "cols"]
+        elif r < 0.13: t = [""]
+        elif r < 0.14: t[5] = "1_0"                               # python 3 int() accepts underscores
+        elif r < 0.15: t[1] = "-%d" % a                           # negative coordinate: floor, not truncation (io.py:55)
+        elif r < 0.16: t[0] = t[3] = "odd chrom name"
+        elif r < 0.17: t[9] = ""                                  # empty trailing field
+        elif r < 0.18: t[2] = "1234567890123456789"               # 19 digits: left to python
+        elif r < 0.19: t[6] = "*"; t[7] = "-1"                    # the "*" / "-1" test looks at every field (io.py:159)
+        lines.append("\t".join(t))
+    return lines
+
+
+def test_native_ingest_equals_line_parser(tmp_path):
+    """cloops_bedpe_parse (+ the per-line class for the lines it hands back) accepts, orients and orders PETs exactly like
+    the per-line restatement of cLoops/io.py:30-59,150-183: plain and gzip input, several files, CRLF, one block or many,
+    one tokenizer or several."""
+    rng = np.random.default_rng(11)
+    f1 = tmp_path / "a.bedpe"
+    f1.write_text("\n".join(_adversarial_lines(rng, 6000)) + "\n")
+    f2 = tmp_path / "b.bedpe.gz"
+    with gzip.open(f2, "wt") as fh:
+        fh.write("\n".join(_adversarial_lines(rng, 5000)))            # no newline at the end
+    f3 = tmp_path / "c.bedpe"
+    f3.write_bytes(("\r\n".join(_adversarial_lines(rng, 3000)) + "\r\n").encode())
+    f4 = tmp_path / "empty.bedpe"
+    f4.write_text("")
+    log = logging.getLogger("t")
+    for fs in ([f1], [f2], [f3], [f4], [f1, f2, f4, f3]):
+        fs = [str(f) for f in fs]
+        for cs, cut in (([], 0), ({"chr1", "chr3", "odd chrom name"}, 0), ([], 5000)):
+            want = list(io._cis_pets(fs, cs, cut, log, True))
+            n_lines = io._cis_pets.total
+            for threads in (1, 5):
+                io.INGEST_THREADS = threads
+                try:
+                    order, per, total = io._cis_native(fs, cs, cut)
+                finally:
+                    io.INGEST_THREADS = 0
+                assert total == n_lines
+                first = {}
+                for c, a, b, o in want:
+                    first.setdefault(c, []).append((a, b, o))
+                assert order == list(first)
+                for c in order:
+                    a, b, opp, line = per[c]
+                    assert list(zip(a.tolist(), b.tolist(), opp.tolist())) == first[c]
+                    assert (np.diff(line) > 0).all()
+    # a carriage return inside a line: declined, the entry points still answer (line-by-line reader)
+    f5 = tmp_path / "cr.bedpe"
+    f5.write_bytes(b"chr1\t1\t3\tchr1\t100\t102\tn\t.\t+\t-\rchr1\t5\t7\tchr1\t200\t202\tn\t.\t+\t-\n")
+    assert io._cis_native([str(f5)], [], 0) is None
+    out = tmp_path / "o"
+    os.mkdir(out)
+    cfs = io.parseRawBedpe2([str(f5)], str(out), [], 0, log)
+    assert io.parseJd(cfs[0])[1].tolist() == [[0, 2, 101], [1, 6, 201]]
+
+
+def test_native_ingest_many_blocks(tmp_path):
+    """A file of many reader blocks (> 4 MB each) with chromosomes interleaved: block stitching keeps file order."""
+    rng = np.random.default_rng(12)
+    n = 400000
+    chrom = rng.integers(1, 24, n)
+    a = rng.integers(0, 2 * 10 ** 8, n)
+    d = rng.integers(0, 10 ** 6, n)
+    with open(tmp_path / "big.bedpe", "w") as fh:
+        fh.write("".join("chr%d\t%d\t%d\tchr%d\t%d\t%d\tread_name_padding_%d\t.\t+\t-\n" % (c, x, x + 36, c, x + y, x + y + 36, k)
+                         for k, (c, x, y) in enumerate(zip(chrom.tolist(), a.tolist(), d.tolist()))))
+    assert os.path.getsize(tmp_path / "big.bedpe") > 5 * (4 << 20)
+    order, per, total = io._cis_native([str(tmp_path / "big.bedpe")], [], 0)
+    assert total == n
+    seen = []
+    for c in chrom.tolist():
+        if "chr%d" % c not in seen:
+            seen.append("chr%d" % c)
+    assert order == seen
+    for c in range(1, 24):
+        m = chrom == c
+        A, B, opp, line = per["chr%d" % c]
+        assert (A == a[m] + 18).all() and (B == a[m] + d[m] + 18).all() and opp.all()
+        assert (line == np.flatnonzero(m)).all()
+
+
+def test_native_ingest_equals_reference(tmp_path):
+    """parseRawBedpe2 / parseRawBedpe + txt2jd of the REFERENCE (cLoops/io.py:62-203, through the shim) against this
+    package's entry points on the reference's bundled chr21 example and on an adversarial file: same .jd files, same
+    matrices, same opposite-strand distances."""
+    if not ref_shim.available():
+        pytest.skip("no reference tree")
+    example = os.path.join(ref_shim.REF_ROOT, "examples", "GSM1872886_GM12878_CTCF_ChIA-PET_chr21_hg38.bedpe.gz")
+    ns = ref_shim.load()
+    rng = np.random.default_rng(13)
+    adv = tmp_path / "adv.bedpe"
+    adv.write_text("\n".join(_adversarial_lines(rng, 5000)) + "\n")
+    log = logging.getLogger("t")
+    cases = [([str(adv)], [], 0), ([str(adv)], ["chr2", "chr4"], 3000)]
+    if os.path.isfile(example):
+        cases += [([example], [], 0), ([example, str(adv)], ["chr21", "chr1"], 1000)]
+    for k, (fs, cs, cut) in enumerate(cases):
+        for dedup in (False, True):
+            ro, mo = tmp_path / ("r%d%d" % (k, dedup)), tmp_path / ("m%d%d" % (k, dedup))
+            os.mkdir(ro); os.mkdir(mo)
+            if dedup:
+                want, want_ds = ns.io.parseRawBedpe(fs, str(ro), cs, cut, log)
+                got, got_ds = io.parseRawBedpe(fs, str(mo), cs, cut, log)
+                assert got_ds == want_ds
+            else:
+                want = ns.io.parseRawBedpe2(fs, str(ro), cs, cut, log)
+                got = io.parseRawBedpe2(fs, str(mo), cs, cut, log)
+            want = [ns.io.txt2jd(f) for f in want]
+            assert [os.path.basename(f) for f in got] == [os.path.basename(f) for f in want]
+            for fw, fg in zip(want, got):
+                w, g = joblib.load(fw), joblib.load(fg)
+                assert g.dtype == np.int64 and np.array_equal(np.asarray(w, dtype=np.int64), g)
+
+
 def test_facade_argument_contract():
     """Errors that are part of the call surface and need no GPU: empty input (cDBSCAN2 -> {},
     v1/block -> IndexError as in cDBSCAN.py:77 / blockDBSCAN.py:74), malformed mat, non-integer eps."""
