@@ -29,6 +29,7 @@ _SIGNATURES = {
     "cloops_stage_count": (C.c_int, []),
     "cloops_stage_name": (C.c_char_p, [C.c_int]),
     "cloops_stage_ms": (C.c_float, [C.c_int]),
+    "cloops_workspace_release": (C.c_int, []),
     "cloops_dbscan": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "cloops_dbscan_host": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _vp]),
     "cloops_neighbour_counts": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),

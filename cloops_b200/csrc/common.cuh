@@ -63,15 +63,37 @@ void stages_begin(cudaStream_t s);            // clears, records "start"
 void stage_mark(const char* name, cudaStream_t s);  // records end of the stage `name`
 int stages_end(cudaStream_t s);               // syncs + resolves ms (profiling only)
 
-// ---- stream-ordered temporary memory ---------------------------------------------------------------
-// cudaMallocAsync from the device's default pool with the release threshold lifted, so steady-state
-// calls re-use cached blocks without touching the driver.
+// ---- temporary memory ----------------------------------------------------------------------------
+// A pass allocates some thirty scratch arrays whose lifetime is one call.  Each (host thread, device, stream) owns a
+// workspace: one device block, handed out by a bump pointer and rewound when the Temp that took the memory goes out of
+// scope (Temps are stack objects, so they nest).  All work that touches the memory is ordered on that stream, which is
+// what makes the rewind safe without a synchronisation.  A request that does not fit opens a further block; when the
+// outermost Temp ends the blocks are replaced by one of the size the call needed, so steady-state calls make no
+// allocator call at all.  CLOOPS_ARENA=0 goes back to one cudaMallocAsync / cudaFreeAsync per array
+// (default pool, release threshold lifted), which is also what every buffer that outlives a call uses.
 int pool_init();
+struct Arena;
+struct ArenaMark {
+    int chunk;
+    size_t off, used;
+};
+Arena* arena_get(cudaStream_t s);                                  // nullptr: workspaces are switched off
+ArenaMark arena_enter(Arena* a);
+void arena_leave(Arena* a, const ArenaMark& m, cudaStream_t s);
+int arena_alloc(Arena* a, size_t bytes, void** out, cudaStream_t s);
+
 struct Temp {
     cudaStream_t s;
+    Arena* a;
+    ArenaMark m;
     std::vector<void*> ptrs;
-    explicit Temp(cudaStream_t st) : s(st) {}
+    explicit Temp(cudaStream_t st) : s(st), a(arena_get(st)) {
+        if (a) m = arena_enter(a);
+    }
+    Temp(const Temp&) = delete;
+    Temp& operator=(const Temp&) = delete;
     ~Temp() {
+        if (a) arena_leave(a, m, s);
         for (void* p : ptrs) cudaFreeAsync(p, s);
     }
     template <class T>
@@ -79,6 +101,11 @@ struct Temp {
         void* p = nullptr;
         size_t bytes = count * sizeof(T);
         if (bytes == 0) bytes = 16;
+        if (a) {
+            RET_IF(arena_alloc(a, bytes, &p, s));
+            *out = (T*)p;
+            return 0;
+        }
         cudaError_t e = cudaMallocAsync(&p, bytes, s);
         if (e != cudaSuccess) return fail(CLOOPS_ENOMEM, "cudaMallocAsync(%zu) failed: %s", bytes, cudaGetErrorString(e));
         ptrs.push_back(p);

@@ -2,6 +2,10 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <map>
+#include <memory>
+#include <mutex>
+
 #include "common.cuh"
 
 namespace cloops {
@@ -70,6 +74,104 @@ int pool_init() {
     return 0;
 }
 
+
+// ---- per-(thread, device, stream) workspaces (see common.cuh) ---------------------------------------------------------
+struct Arena {
+    struct Chunk {
+        char* p;
+        size_t cap;
+    };
+    int dev = 0;
+    std::vector<Chunk> chunks;
+    int cur = 0;               // block the bump pointer is in
+    size_t off = 0;            // bump pointer inside chunks[cur]
+    size_t used = 0;           // bytes handed out and not yet rewound (with the slack left at block ends)
+    size_t high = 0;           // largest `used` since the outermost Temp began
+    int depth = 0;
+};
+
+static const bool g_arena_on = !(getenv("CLOOPS_ARENA") && getenv("CLOOPS_ARENA")[0] == '0');
+static const size_t ARENA_ALIGN = 256, ARENA_MIN_CHUNK = 64u << 20;
+static std::mutex g_arena_mutex;                                   // guards the registry
+static std::vector<Arena*> g_arenas;                               // all workspaces of the process (cloops_workspace_release)
+
+struct ArenaSet {                                                  // the calling thread's workspaces
+    std::map<std::pair<int, cudaStream_t>, Arena*> by_stream;
+    ~ArenaSet() {
+        std::lock_guard<std::mutex> l(g_arena_mutex);
+        for (auto& kv : by_stream) {
+            Arena* a = kv.second;
+            for (Arena::Chunk& c : a->chunks)
+                if (cudaFree(c.p) != cudaSuccess) cudaGetLastError();          // the runtime may already be gone at exit
+            a->chunks.clear();
+            for (size_t k = 0; k < g_arenas.size(); ++k)
+                if (g_arenas[k] == a) { g_arenas.erase(g_arenas.begin() + k); break; }
+            delete a;
+        }
+    }
+};
+static thread_local ArenaSet g_my_arenas;
+
+Arena* arena_get(cudaStream_t s) {
+    if (!g_arena_on) return nullptr;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    Arena*& a = g_my_arenas.by_stream[std::make_pair(dev, s)];
+    if (!a) {
+        a = new Arena();
+        a->dev = dev;
+        std::lock_guard<std::mutex> l(g_arena_mutex);
+        g_arenas.push_back(a);
+    }
+    return a;
+}
+
+ArenaMark arena_enter(Arena* a) {
+    if (a->depth++ == 0) a->high = a->used;
+    return ArenaMark{a->cur, a->off, a->used};
+}
+
+int arena_alloc(Arena* a, size_t bytes, void** out, cudaStream_t s) {
+    bytes = (bytes + ARENA_ALIGN - 1) / ARENA_ALIGN * ARENA_ALIGN;
+    if (a->chunks.empty() || a->off + bytes > a->chunks[a->cur].cap) {
+        // the rest of the current block stays unused until the rewind; take a later block that fits, else add one
+        int k = a->chunks.empty() ? 0 : a->cur + 1;
+        while (k < (int)a->chunks.size() && a->chunks[k].cap < bytes) ++k;
+        if (k == (int)a->chunks.size()) {
+            size_t cap = a->chunks.empty() ? ARENA_MIN_CHUNK : 2 * a->chunks.back().cap;
+            if (cap < bytes) cap = bytes;
+            void* p = nullptr;
+            cudaError_t e = cudaMallocAsync(&p, cap, s);
+            if (e != cudaSuccess) return fail(CLOOPS_ENOMEM, "workspace block of %zu bytes: %s", cap, cudaGetErrorString(e));
+            a->chunks.push_back(Arena::Chunk{(char*)p, cap});
+        }
+        a->cur = k;
+        a->off = 0;
+    }
+    *out = a->chunks[a->cur].p + a->off;
+    a->off += bytes;
+    a->used += bytes;
+    if (a->used > a->high) a->high = a->used;
+    return 0;
+}
+
+void arena_leave(Arena* a, const ArenaMark& m, cudaStream_t s) {
+    a->cur = m.chunk;
+    a->off = m.off;
+    a->used = m.used;
+    if (--a->depth > 0 || a->chunks.size() <= 1) return;
+    // the call needed several blocks: one block that holds its peak from now on (freed and allocated in stream order,
+    // like the work that used them)
+    const size_t want = a->high + a->high / 4;
+    for (Arena::Chunk& c : a->chunks) cudaFreeAsync(c.p, s);
+    a->chunks.clear();
+    a->cur = 0;
+    a->off = a->used = 0;
+    void* p = nullptr;
+    if (cudaMallocAsync(&p, want, s) == cudaSuccess) a->chunks.push_back(Arena::Chunk{(char*)p, want});
+    else cudaGetLastError();                                       // the next request starts from an empty list
+}
+
 }  // namespace cloops
 
 using namespace cloops;
@@ -81,5 +183,23 @@ int64_t cloops_kernel_launches(void) { return (int64_t)g_launches.load(); }
 void cloops_set_profiling(int on) { g_profiling = on != 0; }
 int cloops_stage_count(void) { return g_stages.empty() ? 0 : (int)g_stages.size() - 1; }
 const char* cloops_stage_name(int i) { return (i >= 0 && i + 1 < (int)g_stages.size()) ? g_stages[i + 1].name : ""; }
+int cloops_workspace_release(void) {
+    // frees every workspace block of the process; the caller guarantees that no call is in flight on any thread
+    std::lock_guard<std::mutex> l(g_arena_mutex);
+    int keep = 0;
+    if (cudaGetDevice(&keep) != cudaSuccess) { cudaGetLastError(); return 0; }
+    for (Arena* a : g_arenas) {
+        if (a->chunks.empty()) continue;
+        if (a->depth != 0) return fail(CLOOPS_EINVAL, "a workspace is in use");
+        cudaSetDevice(a->dev);
+        CU_TRY(cudaDeviceSynchronize());
+        for (Arena::Chunk& c : a->chunks) CU_TRY(cudaFree(c.p));
+        a->chunks.clear();
+        a->cur = 0;
+        a->off = a->used = 0;
+    }
+    cudaSetDevice(keep);
+    return 0;
+}
 float cloops_stage_ms(int i) { return (i >= 0 && i + 1 < (int)g_stages.size()) ? g_stages[i + 1].ms : 0.f; }
 }

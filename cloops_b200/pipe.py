@@ -224,7 +224,7 @@ def _cluster_chrom(f, eps, minPts, cut, acc):
 
 #: chromosomes of a round in flight at once on this GPU, each on its own CUDA stream and host thread: while one pass waits
 #: for a size it needs on the host (five short synchronisations per pass), the kernels of another keep the SMs busy
-STREAMS = max(1, int(os.environ.get("CLOOPS_STREAMS", "4")))
+STREAMS = max(1, int(os.environ.get("CLOOPS_STREAMS", "6")))
 _pool = {}
 
 
@@ -557,6 +557,7 @@ def pipe(fs, fout, eps, minPts, chroms="", cpu=1, tmp=0, hic=0, washU=0, juice=0
             log.warning("Something wrong happend to significance estimation, only output called loops")
             ds.to_csv(fout + "_raw.loop", sep="\t", index_label="loopId")
     _Resident.clear()
+    _lib.check(_lib.lib().cloops_workspace_release())          # every pass has been fetched: give the scratch blocks back
     dist.barrier()
     if dist.rank() != 0:
         return

@@ -63,6 +63,10 @@ CLOOPS_API void cloops_set_profiling(int on);
 CLOOPS_API int cloops_stage_count(void);
 CLOOPS_API const char* cloops_stage_name(int i);
 CLOOPS_API float cloops_stage_ms(int i);
+/* Scratch memory of a call comes from a workspace per (host thread, device, stream) that is kept between calls (no allocator
+ * call in steady state; CLOOPS_ARENA=0 in the environment: one cudaMallocAsync per array instead).  This returns every
+ * workspace block of the process to the driver; no call may be in flight on any thread. */
+CLOOPS_API int cloops_workspace_release(void);
 
 /* ---- clustering -------------------------------------------------------------------------------
  * d_x, d_y: int32[n] PET anchor coordinates in ROW order (row = position in the reference's `mat`).

@@ -108,3 +108,42 @@ def test_pass_from_full_index_equals_fresh_build(variant):
                 for a, b in zip(*out):
                     assert np.array_equal(a, b), (eps, mp, cut)
             base.close()
+
+
+def test_workspace_reuse_and_release():
+    """Scratch memory comes from a per-stream workspace that is rewound, grown and replaced between calls: passes of
+    different sizes in a row (small after large, large after small), on two streams, must equal a run in which every
+    call starts from released workspaces -- and cloops_workspace_release must leave the library usable."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from cloops_b200 import _lib, device, synth
+    L = _lib.lib()
+    shapes = [(40_000, 900_000, 5), (600_000, 9_000_000, 6), (3_000, 200_000, 4), (1_200_000, 14_000_000, 8), (600_000, 9_000_000, 6)]
+    data = [synth.chromosome(n, span, seed=100 + k, loop_frac=0.2, sigma=500.0) for k, (n, span, _) in enumerate(shapes)]
+
+    def run(k, stream=None):
+        n, span, mp = shapes[k]
+        X, Y = data[k]
+        with torch.cuda.stream(stream):                      # None: the current stream
+            dx, dy = device.to_device_i32(X), device.to_device_i32(Y)
+            p = device.Pass(dx, dy, 1000, mp, 2, 500 if k % 2 else 0, score=True)
+            bbox, size, kind = p.records()
+            out = (p.n_members, bbox, size, kind, p.labels_sorted.cpu().numpy(), p.counts.cpu().numpy())
+            p.close()
+        return out
+
+    fresh = []
+    for k in range(len(shapes)):
+        _lib.check(L.cloops_workspace_release())
+        fresh.append(run(k))
+    side = torch.cuda.Stream()
+    for order in (range(len(shapes)), reversed(range(len(shapes)))):
+        for k in order:
+            for st in (None, side):
+                got = run(k, st)
+                for a, b in zip(got, fresh[k]):
+                    assert np.array_equal(a, b), (k, st is side)
+    torch.cuda.synchronize()
+    _lib.check(L.cloops_workspace_release())
+    for a, b in zip(run(1), fresh[1]):
+        assert np.array_equal(a, b)
