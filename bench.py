@@ -286,7 +286,7 @@ def workload_config(cfg, args, world):
     c = {"workload": cfg["name"], "config": args.config, "pets_total": args.pets * (world if cfg["kind"] == "single" else 1),
          "eps": cfg["eps"], "minPts": cfg["minPts"], "rounds": len(cfg["eps"]) * len(cfg["minPts"]), "clusterer": "cDBSCAN2",
          "l2": "256 MiB buffer written between timed steps; inputs (>= 80 MB per chromosome) exceed L2",
-         "streams": "up to %s chromosomes of a rank in flight on separate CUDA streams (CLOOPS_STREAMS); stage and roofline times are taken with one" % os.environ.get("CLOOPS_STREAMS", "4")}
+         "streams": "up to %s chromosomes of a rank in flight on separate CUDA streams (CLOOPS_STREAMS); stage and roofline times are taken with one" % os.environ.get("CLOOPS_STREAMS", "6")}
     if cfg["kind"] == "genome":
         c["sharding"] = "23 hg38-proportional chromosomes packed onto %d rank(s) by PET count (LPT); one NCCL all-reduce of the cut-off statistics per round" % world
     elif cfg["kind"] == "single":
@@ -489,6 +489,7 @@ def main():
     # stage times of the library's kernels, live, on the same stream, in separate steps (the event synchronisations of the
     # profiling mode would perturb `value`)
     streams_saved, pipe.STREAMS = pipe.STREAMS, 1          # one chromosome at a time: a kernel's events then bracket that kernel alone
+    step_dev()                                             # untimed: this thread's scratch workspace grows to its steady size
     device.Profile.begin()
     flush.fill_(1)
     step_dev()
