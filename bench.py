@@ -541,6 +541,7 @@ def main():
                                  "definition": "8 B x (PETs with X in the hull of a candidate's windows + PETs with Y in it) + 4 B per output integer (SURVEY 8d)"},
         "stages_ms": {k: round(v, 3) for k, v in sorted(stages.items(), key=lambda kv: -kv[1])},
         "rank_balance": {"slowest_ms": t_dev, "fastest_ms": t_min},
+        "step_ms": {"value": [round(v, 1) for v in ms], "e2e": [round(v, 1) for v in ms_e2e], "of": "rank 0"},
     }
     line.update(extra)
     if cfg["kind"] != "sweep":

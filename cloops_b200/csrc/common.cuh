@@ -78,7 +78,8 @@ struct ArenaMark {
     size_t off, used;
 };
 Arena* arena_get(cudaStream_t s);                                  // nullptr: workspaces are switched off
-ArenaMark arena_enter(Arena* a);
+enum { WS_MISC = 0, WS_PASS = 1 };                                 // WS_PASS: the outermost Temp of a whole per-chromosome pass
+ArenaMark arena_enter(Arena* a, cudaStream_t s, int kind);
 void arena_leave(Arena* a, const ArenaMark& m, cudaStream_t s);
 int arena_alloc(Arena* a, size_t bytes, void** out, cudaStream_t s);
 
@@ -87,8 +88,8 @@ struct Temp {
     Arena* a;
     ArenaMark m;
     std::vector<void*> ptrs;
-    explicit Temp(cudaStream_t st) : s(st), a(arena_get(st)) {
-        if (a) m = arena_enter(a);
+    explicit Temp(cudaStream_t st, int kind = WS_MISC) : s(st), a(arena_get(st)) {
+        if (a) m = arena_enter(a, st, kind);
     }
     Temp(const Temp&) = delete;
     Temp& operator=(const Temp&) = delete;

@@ -114,6 +114,7 @@ static int pass_run(cloops_pass* p, const int32_t* d_x, const int32_t* d_y, int6
     p->n = (int)n;
     if (n == 0) return 0;
     RET_IF(pool_init());
+    Temp scope(st, WS_PASS);                       // the scratch arrays of every stage below come from one workspace, settled once per pass
     cloops_coverage* cov = nullptr;
     Side* side = nullptr;
     int rc = 0;

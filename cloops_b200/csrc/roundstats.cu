@@ -25,13 +25,14 @@ __global__ void __launch_bounds__(256) count_inter_kernel(const unsigned char* _
 
 // members: [n_members] (X, Y, kind) of the clustered PETs (index order, or row order for blockDBSCAN);
 // raw: [n_raw] the chromosome's rows, scanned for the ones the cut filter removed (signed Y-X < cut), only when cut > 0.
-__global__ void __launch_bounds__(256) dist_stats_kernel(const int* __restrict__ xs, const int* __restrict__ ys,
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) dist_stats_kernel(const int* __restrict__ xs, const int* __restrict__ ys,
                                                          const unsigned char* __restrict__ member_kind, int n_members,
                                                          const int* __restrict__ raw_x, const int* __restrict__ raw_y, int n_raw, int cut,
                                                          const int* __restrict__ n_inter, int* __restrict__ hist,
                                                          double* __restrict__ partial) {
     __shared__ int s_hist[RS_LOCAL];
-    __shared__ double s_red[8][RS_NQ];
+    __shared__ double s_red[THREADS / 32][RS_NQ];
     if (*n_inter == 0) return;                                     // pipe.py:121-122
     for (int t = threadIdx.x; t < RS_LOCAL; t += blockDim.x) s_hist[t] = 0;
     __syncthreads();
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(256) dist_stats_kernel(const int* __restrict__
     __syncthreads();
     if (threadIdx.x < RS_NQ) {
         double v = 0;
-        for (int w = 0; w < 8; ++w) v += s_red[w][threadIdx.x];    // fixed order: the sums are reproducible
+        for (int w = 0; w < THREADS / 32; ++w) v += s_red[w][threadIdx.x];    // fixed order: the sums are reproducible
         partial[blockIdx.x * RS_NQ + threadIdx.x] = v;
     }
     for (int t = threadIdx.x; t < RS_LOCAL; t += blockDim.x)
@@ -158,8 +159,13 @@ int pass_distance_stats(const int* xs, const int* ys, const unsigned char* membe
     RET_IF(tmp.alloc(&d_partial, (size_t)RS_GRID * RS_NQ));
     CU_TRY(cudaMemsetAsync(d_ninter, 0, sizeof(int), st));
     if (k > 0) LAUNCH(count_inter_kernel, cdiv(k, 256), 256, 0, st, kind, k, d_ninter);
-    LAUNCH(dist_stats_kernel, RS_GRID, 256, 0, st, xs, ys, member_kind, n_members, raw_x, raw_y, n_raw, cut, d_ninter, d_hist, d_partial);
-    LAUNCH(dist_stats_commit_kernel, 1, 32 * RS_NQ, 0, st, d_partial, RS_GRID, d_ninter, d_mom);
+    // every CTA ends by adding its non-empty shared bins to the global histogram: fewer, larger CTAs mean fewer of those
+    // atomics (CLOOPS_RS_WIDE=0: 592 CTAs of 256 threads, the form measured first)
+    static const bool wide = !(getenv("CLOOPS_RS_WIDE") && getenv("CLOOPS_RS_WIDE")[0] == '0');
+    const int grid = wide ? RS_GRID / 4 : RS_GRID;
+    if (wide) LAUNCH(dist_stats_kernel<1024>, grid, 1024, 0, st, xs, ys, member_kind, n_members, raw_x, raw_y, n_raw, cut, d_ninter, d_hist, d_partial);
+    else LAUNCH(dist_stats_kernel<256>, grid, 256, 0, st, xs, ys, member_kind, n_members, raw_x, raw_y, n_raw, cut, d_ninter, d_hist, d_partial);
+    LAUNCH(dist_stats_commit_kernel, 1, 32 * RS_NQ, 0, st, d_partial, grid, d_ninter, d_mom);
     return 0;
 }
 

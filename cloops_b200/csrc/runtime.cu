@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <chrono>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -88,9 +89,11 @@ struct Arena {
     size_t used = 0;           // bytes handed out and not yet rewound (with the slack left at block ends)
     size_t high = 0;           // largest `used` since the outermost Temp began
     int depth = 0;
+    int kind = 0;              // what the outermost Temp of the current call said it is for (WS_*)
 };
 
 static const bool g_arena_on = !(getenv("CLOOPS_ARENA") && getenv("CLOOPS_ARENA")[0] == '0');
+static const bool g_arena_trace = getenv("CLOOPS_TRACE") != nullptr;
 static const size_t ARENA_ALIGN = 256, ARENA_MIN_CHUNK = 64u << 20;
 static std::mutex g_arena_mutex;                                   // guards the registry
 static std::vector<Arena*> g_arenas;                               // all workspaces of the process (cloops_workspace_release)
@@ -126,8 +129,34 @@ Arena* arena_get(cudaStream_t s) {
     return a;
 }
 
-ArenaMark arena_enter(Arena* a) {
-    if (a->depth++ == 0) a->high = a->used;
+// largest peak any whole-pass workspace (WS_PASS) of the process has seen, per device: a thread that has only served small
+// chromosomes so far sizes its block for the largest one before it meets it, so that all blocks reach their final size in
+// the first round instead of one at a time over many calls (a late gigabyte-sized cudaMallocAsync was measured at 0.4 s)
+static std::atomic<size_t> g_arena_peak[64];
+
+static size_t arena_target(const Arena* a) {
+    if (a->kind != WS_PASS) return 0;
+    const size_t peak = g_arena_peak[a->dev & 63].load(std::memory_order_relaxed);
+    return peak + peak / 4;
+}
+
+ArenaMark arena_enter(Arena* a, cudaStream_t s, int kind) {
+    if (a->depth++ == 0) {
+        a->kind = kind;
+        a->high = a->used;
+        const size_t want = arena_target(a);
+        if (a->chunks.size() <= 1 && want > (a->chunks.empty() ? 0 : a->chunks[0].cap) && want >= ARENA_MIN_CHUNK) {
+            const auto t0 = std::chrono::steady_clock::now();
+            if (!a->chunks.empty()) cudaFreeAsync(a->chunks[0].p, s);
+            a->chunks.clear();
+            void* p = nullptr;
+            if (cudaMallocAsync(&p, want, s) == cudaSuccess) a->chunks.push_back(Arena::Chunk{(char*)p, want});
+            else cudaGetLastError();
+            if (g_arena_trace)
+                fprintf(stderr, "[cloops] workspace %p: block of %zu MB for the process-wide peak in %.2f ms\n", (void*)a, want >> 20,
+                        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+        }
+    }
     return ArenaMark{a->cur, a->off, a->used};
 }
 
@@ -140,9 +169,14 @@ int arena_alloc(Arena* a, size_t bytes, void** out, cudaStream_t s) {
         if (k == (int)a->chunks.size()) {
             size_t cap = a->chunks.empty() ? ARENA_MIN_CHUNK : 2 * a->chunks.back().cap;
             if (cap < bytes) cap = bytes;
+            if (cap < arena_target(a)) cap = arena_target(a);
             void* p = nullptr;
+            const auto t0 = std::chrono::steady_clock::now();
             cudaError_t e = cudaMallocAsync(&p, cap, s);
             if (e != cudaSuccess) return fail(CLOOPS_ENOMEM, "workspace block of %zu bytes: %s", cap, cudaGetErrorString(e));
+            if (g_arena_trace)
+                fprintf(stderr, "[cloops] workspace %p: block %d of %zu MB in %.2f ms\n", (void*)a, (int)a->chunks.size(), cap >> 20,
+                        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
             a->chunks.push_back(Arena::Chunk{(char*)p, cap});
         }
         a->cur = k;
@@ -151,7 +185,14 @@ int arena_alloc(Arena* a, size_t bytes, void** out, cudaStream_t s) {
     *out = a->chunks[a->cur].p + a->off;
     a->off += bytes;
     a->used += bytes;
-    if (a->used > a->high) a->high = a->used;
+    if (a->used > a->high) {
+        a->high = a->used;
+        if (a->kind == WS_PASS) {
+            std::atomic<size_t>& peak = g_arena_peak[a->dev & 63];
+            size_t seen = peak.load(std::memory_order_relaxed);
+            while (a->high > seen && !peak.compare_exchange_weak(seen, a->high, std::memory_order_relaxed)) {}
+        }
+    }
     return 0;
 }
 
@@ -162,7 +203,9 @@ void arena_leave(Arena* a, const ArenaMark& m, cudaStream_t s) {
     if (--a->depth > 0 || a->chunks.size() <= 1) return;
     // the call needed several blocks: one block that holds its peak from now on (freed and allocated in stream order,
     // like the work that used them)
-    const size_t want = a->high + a->high / 4;
+    size_t want = a->high + a->high / 4;
+    if (want < arena_target(a)) want = arena_target(a);
+    const auto t0 = std::chrono::steady_clock::now();
     for (Arena::Chunk& c : a->chunks) cudaFreeAsync(c.p, s);
     a->chunks.clear();
     a->cur = 0;
@@ -170,6 +213,9 @@ void arena_leave(Arena* a, const ArenaMark& m, cudaStream_t s) {
     void* p = nullptr;
     if (cudaMallocAsync(&p, want, s) == cudaSuccess) a->chunks.push_back(Arena::Chunk{(char*)p, want});
     else cudaGetLastError();                                       // the next request starts from an empty list
+    if (g_arena_trace)
+        fprintf(stderr, "[cloops] workspace %p: one block of %zu MB in %.2f ms\n", (void*)a, want >> 20,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
 }
 
 }  // namespace cloops
@@ -198,6 +244,7 @@ int cloops_workspace_release(void) {
         a->cur = 0;
         a->off = a->used = 0;
     }
+    for (std::atomic<size_t>& p : g_arena_peak) p.store(0);
     cudaSetDevice(keep);
     return 0;
 }

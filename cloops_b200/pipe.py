@@ -225,16 +225,26 @@ def _cluster_chrom(f, eps, minPts, cut, acc):
 #: chromosomes of a round in flight at once on this GPU, each on its own CUDA stream and host thread: while one pass waits
 #: for a size it needs on the host (five short synchronisations per pass), the kernels of another keep the SMs busy
 STREAMS = max(1, int(os.environ.get("CLOOPS_STREAMS", "6")))
+LARGEST_FIRST = os.environ.get("CLOOPS_LARGEST_FIRST", "1") != "0"
 _pool = {}
 
 
-def _on_streams(items, fn):
+def _on_streams(items, fn, sizes=None):
     """[fn(item) for item in items], up to STREAMS of them in flight, each host thread on a CUDA stream of its own (the
-    streams wait for the caller's stream first and the caller's stream waits for them afterwards)."""
+    streams wait for the caller's stream first and the caller's stream waits for them afterwards).  With ``sizes`` the
+    largest items start first, so that the call does not end on one large item running alone (CLOOPS_LARGEST_FIRST=0:
+    list order); the results come back in list order either way."""
     import torch
     items = list(items)
     if STREAMS <= 1 or len(items) <= 1 or not torch.cuda.is_available():
         return [fn(it) for it in items]
+    if sizes is not None and LARGEST_FIRST:
+        order = sorted(range(len(items)), key=lambda k: -sizes[k])
+        back = _on_streams([items[k] for k in order], fn)
+        out = [None] * len(items)
+        for k, r in zip(order, back):
+            out[k] = r
+        return out
     from concurrent.futures import ThreadPoolExecutor
     dev = torch.cuda.current_device()
     if "ex" not in _pool:
@@ -264,7 +274,7 @@ def _cluster_many(files, eps, minPts, cut, acc):
     """_cluster_chrom for every file, results in file order."""
     if not acc.hist.is_cuda:
         return [_cluster_chrom(f, eps, minPts, cut, acc) for f in files]
-    return _on_streams(files, lambda f: _cluster_chrom(f, eps, minPts, cut, acc))
+    return _on_streams(files, lambda f: _cluster_chrom(f, eps, minPts, cut, acc), sizes=[_Resident.get(f).n for f in files])
 
 
 def _round(fs, eps, minPts, cut, weights=None):
@@ -471,7 +481,9 @@ def call_loops(cfs, eps, minPts, hic=0, cut=0, max_cut=False, weights=None, tail
     # candidate merging of chromosome k+1 (host C++, releases the GIL) runs while the GPU counts chromosome k; with
     # ``tail`` the statistics tail of a chromosome (host threads) runs while the GPU counts the next ones
     with ThreadPoolExecutor(max_workers=1) as prep, ThreadPoolExecutor(max_workers=max(1, min(6, (os.cpu_count() or 2) // 2))) as ex:
-        ready = {k: prep.submit(_finalize_records, dataI[k], cut) for k in dataI}
+        work = {k: sum(len(r) for r in dataI[k]["rounds"]) if "rounds" in dataI[k] else len(dataI[k]["records"]) for k in dataI}
+        first = sorted(dataI, key=lambda k: -work[k]) if LARGEST_FIRST else list(dataI)      # the order the GPU takes them in
+        ready = {k: prep.submit(_finalize_records, dataI[k], cut) for k in first}
         futs = {}
 
         def count_one(k):
@@ -482,7 +494,7 @@ def call_loops(cfs, eps, minPts, hic=0, cut=0, max_cut=False, weights=None, tail
             return c
 
         keys = list(dataI)
-        counted = dict(zip(keys, _on_streams(keys, count_one)))
+        counted = dict(zip(keys, _on_streams(keys, count_one, sizes=[work[k] for k in keys])))
         if not tail:
             out["counted"] = counted
             return out
