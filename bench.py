@@ -543,6 +543,9 @@ def main():
         "rank_balance": {"slowest_ms": t_dev, "fastest_ms": t_min},
         "step_ms": {"value": [round(v, 1) for v in ms], "e2e": [round(v, 1) for v in ms_e2e], "of": "rank 0"},
     }
+    host_ms = res.get("h", {}).get("host_ms") if isinstance(res.get("h"), dict) else None
+    if host_ms:                                            # where the host thread of the last e2e step spent its wall-clock (after the H2D copy)
+        line["e2e"]["host_ms_last_step"] = {k: round(v, 1) for k, v in host_ms.items()}
     line.update(extra)
     if cfg["kind"] != "sweep":
         r, h = res["r"], res["h"]

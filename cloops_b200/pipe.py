@@ -472,7 +472,10 @@ def call_loops(cfs, eps, minPts, hic=0, cut=0, max_cut=False, weights=None, tail
     (every rank), ``weights`` their PET counts; each rank works on its own share.
     -> dict(cut, dataI, counted, table)"""
     from concurrent.futures import ThreadPoolExecutor
+    import time
+    t0 = time.perf_counter()
     dataI, cut = _rounds(cfs, eps, minPts, cut, max_cut, _log(), weights, finalize=False)
+    t1 = time.perf_counter()
     for k, f in enumerate(cfs):
         key = tuple(os.path.split(f)[1].replace("mem:", "").replace(".jd", "").split("-"))
         if key in dataI:
@@ -495,13 +498,21 @@ def call_loops(cfs, eps, minPts, hic=0, cut=0, max_cut=False, weights=None, tail
 
         keys = list(dataI)
         counted = dict(zip(keys, _on_streams(keys, count_one, sizes=[work[k] for k in keys])))
+        t2 = time.perf_counter()
         if not tail:
             out["counted"] = counted
+            out["host_ms"] = {"rounds": (t1 - t0) * 1e3, "range_counts": (t2 - t1) * 1e3}
             return out
         tables = {k: futs[k].result() for k in keys}
+    t3 = time.perf_counter()
     ds = _tables(dataI, tables, _local=True, done=True)
+    t4 = time.perf_counter()
     if ds is not None:
         out["table"] = (markIntSigHic(ds) if hic else markIntSig(ds)) if mark else ds
+    # wall-clock of the host thread: clustering rounds; range counts (with the statistics tails of the chromosomes counted
+    # first running beside them); what is left of the tails once the GPU is done; table gather; significance marks
+    out["host_ms"] = {"rounds": (t1 - t0) * 1e3, "range_counts": (t2 - t1) * 1e3, "tail_after_gpu": (t3 - t2) * 1e3,
+                      "tables": (t4 - t3) * 1e3, "marks": (time.perf_counter() - t4) * 1e3}
     return out
 
 
