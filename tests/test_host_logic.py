@@ -295,6 +295,9 @@ def test_native_ingest_equals_line_parser(tmp_path):
                     a, b, opp, line = per[c]
                     assert list(zip(a.tolist(), b.tolist(), opp.tolist())) == first[c]
                     assert (np.diff(line) > 0).all()
+    from cloops_b200._lib import CloopsError
+    with pytest.raises(CloopsError, match="cannot open"):      # the reference raises IOError from open() (io.py:150-151)
+        io._cis_native([str(tmp_path / "missing.bedpe")], [], 0)
     # a carriage return inside a line: declined, the entry points still answer (line-by-line reader)
     f5 = tmp_path / "cr.bedpe"
     f5.write_bytes(b"chr1\t1\t3\tchr1\t100\t102\tn\t.\t+\t-\rchr1\t5\t7\tchr1\t200\t202\tn\t.\t+\t-\n")
