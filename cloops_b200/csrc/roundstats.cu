@@ -2,9 +2,13 @@
 // cLoops/ests.py:36-61).  The reference pools two Python lists over all chromosomes -- dis: Y-X of the members of
 // inter-ligation clusters; dss: Y-X of the rows removed by the cut filter plus the members of self-ligation clusters --
 // and derives the next round's distance cut-off from the mean / std / median of their log2.  Here every chromosome adds
-// to one accumulator per round: (count, sum, sum of squares) of log2|d| in float64 and an exact histogram of the positive
-// self-ligation distances (the median is an order statistic; log2 is monotone).  Across GPUs the accumulators are
-// all-reduced (NCCL) -- 4 MB instead of the distance lists themselves.
+// to one accumulator per round: an exact histogram of the positive self-ligation distances (the median is an order
+// statistic; log2 is monotone) and (count, sum, sum of squares) of log2|d| in float64 for the inter-ligation distances.
+// The same three moments of the self-ligation distances are NOT accumulated per PET: they follow from the histogram
+// (sum over bins of count * log2(bin)), evaluated once per round in cloops_round_middle -- 2^20 logarithms per round
+// instead of one per removed / self-ligation PET per chromosome (ncu: the per-PET float64 log2 made the kernel
+// instruction-bound, 100 M warp instructions for 23 M rows); only distances beyond the histogram (>= 2^20) keep their
+// per-PET terms.  Across GPUs the accumulators are all-reduced (NCCL) -- 4 MB instead of the distance lists themselves.
 //
 // A chromosome without inter-ligation clusters contributes nothing, not even its dss (pipe.py:121-122): the kernels
 // read the chromosome's inter-ligation cluster count on the device and return early.
@@ -50,15 +54,16 @@ __global__ void __launch_bounds__(THREADS) dist_stats_kernel(const int* __restri
         }
         if (which == 0) continue;
         const unsigned a = (unsigned)(d < 0 ? -d : d);              // ests.py:40-41 np.abs
-        const int o = which == 1 ? 0 : 3;
-        q[6 + (which == 1 ? 0 : 1)] += 1.0;
+        if (which == 1) q[6] += 1.0; else q[7] += 1.0;
         if (a == 0) continue;                                      // ests.py:44-45: zero distances are dropped
-        const double lg = log2((double)a);
-        q[o] += 1.0; q[o + 1] += lg; q[o + 2] += lg * lg;
         if (which == 2) {
-            if (a < RS_LOCAL) atomicAdd(&s_hist[a], 1);
-            else atomicAdd(&hist[a < RS_BINS ? a : RS_BINS], 1);
+            if (a < RS_LOCAL) { atomicAdd(&s_hist[a], 1); continue; }
+            if (a < RS_BINS) { atomicAdd(&hist[a], 1); continue; }
+            atomicAdd(&hist[RS_BINS], 1);                          // beyond the histogram: counted there, moments per PET
         }
+        const double lg = log2((double)a);
+        if (which == 1) { q[0] += 1.0; q[1] += lg; q[2] += lg * lg; }
+        else { q[3] += 1.0; q[4] += lg; q[5] += lg * lg; }
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -77,7 +82,8 @@ __global__ void __launch_bounds__(THREADS) dist_stats_kernel(const int* __restri
         if (s_hist[t]) atomicAdd(&hist[t], s_hist[t]);
 }
 
-// mom: 0 n_i, 1 S_i, 2 Q_i, 3 n_s, 4 S_s, 5 Q_s, 6 len(dis), 7 len(dss), 8 chromosomes with inter-ligation clusters
+// mom: 0 n_i, 1 S_i, 2 Q_i, 3..5 the same for the self-ligation distances >= 2^20 only (the rest is in the histogram),
+// 6 len(dis), 7 len(dss), 8 chromosomes with inter-ligation clusters
 __global__ void __launch_bounds__(32 * RS_NQ) dist_stats_commit_kernel(const double* __restrict__ partial, int nblocks, const int* __restrict__ n_inter,
                                                                        double* __restrict__ mom) {
     if (*n_inter == 0) return;
@@ -89,64 +95,98 @@ __global__ void __launch_bounds__(32 * RS_NQ) dist_stats_commit_kernel(const dou
     if (threadIdx.x == 0) atomicAdd(&mom[8], 1.0);
 }
 
-// The two middle order statistics of the histogrammed values: out[0] = value of rank (k-1)/2, out[1] = value of rank k/2
-// (0-based), k = mom[3]; -1 when k == 0, RS_BINS when the rank lies in the overflow bin.  Two launches: sums of 1024-bin
-// chunks (coalesced), then one CTA scans the chunk sums, finds the chunk of each rank and scans that chunk.
+// Order statistics and moments of the histogrammed self-ligation distances.  Two launches: per 1024-bin chunk the count
+// and the two log2 sums (coalesced, fixed summation order); then one CTA scans the chunk counts, finds the chunk of each
+// middle rank and scans that chunk, and adds up the chunk sums.
+// out[0] = value of rank (k-1)/2, out[1] = value of rank k/2 (0-based; k = number of histogrammed values, overflow bin
+// included); -1 when k == 0, RS_BINS when the rank lies in the overflow bin.  out[2] = k.  sums[0..1] = sum of log2 and of
+// log2^2 over the values below 2^20.
 #define RS_CHUNK 1024
 #define RS_NCHUNK ((RS_BINS + 1 + RS_CHUNK - 1) / RS_CHUNK)
-__global__ void __launch_bounds__(256) hist_chunk_kernel(const int* __restrict__ hist, long long* __restrict__ chunk) {
+__global__ void __launch_bounds__(256) hist_chunk_kernel(const int* __restrict__ hist, long long* __restrict__ chunk, double* __restrict__ csum) {
     __shared__ long long s_w[8];
+    __shared__ double s_s[8], s_q[8];
     long long v = 0;
+    double sl = 0, sq = 0;
     for (int t = threadIdx.x; t < RS_CHUNK; t += 256) {
         const int b = blockIdx.x * RS_CHUNK + t;
-        if (b <= RS_BINS) v += hist[b];
+        if (b > RS_BINS) continue;
+        const int c = hist[b];
+        v += c;
+        if (c && b >= 1 && b < RS_BINS) {
+            const double lg = log2((double)b);
+            sl += c * lg;
+            sq += c * (lg * lg);
+        }
     }
-    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
-    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
+    for (int off = 16; off > 0; off >>= 1) {
+        v += __shfl_down_sync(0xffffffffu, v, off);
+        sl += __shfl_down_sync(0xffffffffu, sl, off);
+        sq += __shfl_down_sync(0xffffffffu, sq, off);
+    }
+    if ((threadIdx.x & 31) == 0) { s_w[threadIdx.x >> 5] = v; s_s[threadIdx.x >> 5] = sl; s_q[threadIdx.x >> 5] = sq; }
     __syncthreads();
     if (threadIdx.x == 0) {
         long long tot = 0;
-        for (int w = 0; w < 8; ++w) tot += s_w[w];
+        double a = 0, b = 0;
+        for (int w = 0; w < 8; ++w) { tot += s_w[w]; a += s_s[w]; b += s_q[w]; }
         chunk[blockIdx.x] = tot;
+        csum[2 * blockIdx.x] = a;
+        csum[2 * blockIdx.x + 1] = b;
+    }
+}
+
+// inclusive scan of s[0..1023] in place (1024 threads); the caller synchronises before reading
+__device__ __forceinline__ void scan1024(long long* s) {
+    for (int d = 1; d < 1024; d <<= 1) {
+        const long long add = (int)threadIdx.x >= d ? s[threadIdx.x - d] : 0;
+        __syncthreads();
+        s[threadIdx.x] += add;
+        __syncthreads();
     }
 }
 
 __global__ void __launch_bounds__(1024) hist_middle_kernel(const int* __restrict__ hist, const long long* __restrict__ chunk,
-                                                           const double* __restrict__ mom, long long* __restrict__ out) {
-    __shared__ long long s_before[RS_NCHUNK + 1];
-    __shared__ int s_bins[RS_CHUNK];
-    const long long k = (long long)mom[3];
+                                                           const double* __restrict__ csum, long long* __restrict__ out,
+                                                           double* __restrict__ sums) {
+    __shared__ long long s_incl[1024];                       // inclusive counts of chunks 0..1023 (chunk 1024 = the overflow bin alone)
+    __shared__ long long s_bins[RS_CHUNK];
+    const int tid = threadIdx.x;
+    s_incl[tid] = chunk[tid];
+    __syncthreads();
+    scan1024(s_incl);
+    const long long k = s_incl[1023] + chunk[RS_NCHUNK - 1];
+    if (tid < 64) {                                          // chunk sums: warp 0 the log2 sums, warp 1 the squares; fixed order
+        const int which = tid >> 5, lane = tid & 31;
+        double v = 0;
+        for (int c = lane; c < RS_NCHUNK; c += 32) v += csum[2 * c + which];
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+        if (lane == 0) sums[which] = v;
+    }
+    if (tid == 0) out[2] = k;
     if (k == 0) {
-        if (threadIdx.x == 0) { out[0] = -1; out[1] = -1; }
+        if (tid == 0) { out[0] = -1; out[1] = -1; }
         return;
     }
-    if (threadIdx.x == 0) {                                  // 1025 chunk sums: a serial prefix is a microsecond
-        long long acc = 0;
-        for (int c = 0; c < RS_NCHUNK; ++c) { s_before[c] = acc; acc += chunk[c]; }
-        s_before[RS_NCHUNK] = acc;
-    }
-    __syncthreads();
     for (int w = 0; w < 2; ++w) {
         const long long r = w == 0 ? (k - 1) / 2 : k / 2;
-        int c = 0;                                           // chunk holding rank r (every thread finds it: uniform)
-        for (int lo = 0, hi = RS_NCHUNK; lo < hi;) {
+        int lo = 0, hi = 1024;                               // first chunk whose inclusive count exceeds r (1024: the overflow bin)
+        while (lo < hi) {
             const int mid = (lo + hi) >> 1;
-            if (s_before[mid + 1] <= r) lo = mid + 1; else hi = mid;
-            c = lo;
+            if (s_incl[mid] <= r) lo = mid + 1; else hi = mid;
         }
-        const int b = c * RS_CHUNK + threadIdx.x;
-        s_bins[threadIdx.x] = b <= RS_BINS ? hist[b] : 0;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            long long acc = s_before[c];
-            long long val = RS_BINS;
-            for (int t = 0; t < RS_CHUNK; ++t) {
-                acc += s_bins[t];
-                if (r < acc) { val = (long long)c * RS_CHUNK + t; break; }
-            }
-            out[w] = val;
+        const int c = lo;
+        if (c == 1024) {
+            if (tid == 0) out[w] = RS_BINS;
+            continue;
         }
+        const long long before = c ? s_incl[c - 1] : 0;
         __syncthreads();
+        s_bins[tid] = hist[c * RS_CHUNK + tid];
+        __syncthreads();
+        scan1024(s_bins);
+        const long long incl = s_bins[tid], excl = tid ? s_bins[tid - 1] : 0;
+        if (before + excl <= r && r < before + incl) out[w] = (long long)c * RS_CHUNK + tid;
     }
 }
 
@@ -179,15 +219,25 @@ extern "C" int cloops_round_middle(const int32_t* d_hist, const double* d_mom, i
     RET_IF(pool_init());
     Temp tmp(st);
     long long *d_out, *d_chunk;
-    RET_IF(tmp.alloc(&d_out, 2));
+    double *d_csum, *d_sums;
+    RET_IF(tmp.alloc(&d_out, 3));
     RET_IF(tmp.alloc(&d_chunk, RS_NCHUNK));
-    LAUNCH(hist_chunk_kernel, RS_NCHUNK, 256, 0, st, d_hist, d_chunk);
-    LAUNCH(hist_middle_kernel, 1, 1024, 0, st, d_hist, d_chunk, d_mom, d_out);
-    long long out[2];
+    RET_IF(tmp.alloc(&d_csum, 2 * RS_NCHUNK));
+    RET_IF(tmp.alloc(&d_sums, 2));
+    LAUNCH(hist_chunk_kernel, RS_NCHUNK, 256, 0, st, d_hist, d_chunk, d_csum);
+    LAUNCH(hist_middle_kernel, 1, 1024, 0, st, d_hist, d_chunk, d_csum, d_out, d_sums);
+    long long out[3];
+    double sums[2];
     CU_TRY(cudaMemcpyAsync(out, d_out, sizeof(out), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(sums, d_sums, sizeof(sums), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaMemcpyAsync(h_mom, d_mom, CLOOPS_ROUND_MOM * sizeof(double), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
     h_middle[0] = out[0];
     h_middle[1] = out[1];
+    // the self-ligation moments: every positive distance is in the histogram (out[2] of them); the accumulators hold the
+    // log2 terms of the ones beyond it, the histogram gives the rest
+    h_mom[3] = (double)out[2];
+    h_mom[4] += sums[0];
+    h_mom[5] += sums[1];
     return 0;
 }

@@ -150,9 +150,11 @@ CLOOPS_API int cloops_pass_run(const int32_t* d_x, const int32_t* d_y, int64_t n
 /* The same pass, additionally adding this chromosome's distance statistics to the accumulators of the current clustering
  * round (replaces the dis / dss lists of cLoops/pipe.py:59-63,106-109 pooled at pipe.py:120-127 and reduced by
  * cLoops/ests.py:36-61): d_hist int32[CLOOPS_ROUND_HIST_BINS + 1] = exact histogram of the positive self-ligation distances
- * (last bin = overflow), d_mom double[CLOOPS_ROUND_MOM] = n, sum, sum of squares of log2|d| for the inter- (0..2) and
- * self-ligation (3..5) sets, len(dis), len(dss) (6, 7), chromosomes that contributed (8).  A chromosome without inter-ligation
- * clusters adds nothing (pipe.py:121-122).  The caller zeroes the accumulators per round and sums them over GPUs. */
+ * (last bin = overflow), d_mom double[CLOOPS_ROUND_MOM] = n, sum, sum of squares of log2|d| for the inter-ligation set (0..2)
+ * and for the self-ligation distances BEYOND the histogram only (3..5; the moments of the histogrammed ones follow from the
+ * histogram and are added by cloops_round_middle), len(dis), len(dss) (6, 7), chromosomes that contributed (8).  A chromosome
+ * without inter-ligation clusters adds nothing (pipe.py:121-122).  The caller zeroes the accumulators per round and sums them
+ * over GPUs. */
 #define CLOOPS_ROUND_HIST_BINS (1 << 20)
 #define CLOOPS_ROUND_MOM 16
 CLOOPS_API int cloops_pass_run_stats(const int32_t* d_x, const int32_t* d_y, int64_t n, int32_t eps, int32_t minPts, int32_t cut,
@@ -163,9 +165,11 @@ CLOOPS_API int cloops_pass_run_stats(const int32_t* d_x, const int32_t* d_y, int
  * -m 3 / -m 4 (cLoops/pipe.py:337-344) cluster every eps with 2-4 minPts values, each with the cut of the round before. */
 CLOOPS_API int cloops_pass_run_base(const cloops_index* base, const int32_t* d_x, const int32_t* d_y, int64_t n, int32_t minPts,
                          int32_t cut, int32_t variant, int32_t score, int32_t* d_hist, double* d_mom, cloops_pass** out, void* stream);
-/* The two middle order statistics of the histogram (ranks (k-1)/2 and k/2 of the k = d_mom[3] positive self-ligation
- * distances; -1 if k = 0, CLOOPS_ROUND_HIST_BINS if a rank lies in the overflow bin) and a host copy of d_mom: what
- * estIntSelCutFrag (cLoops/ests.py:36-61) needs.  Synchronises the stream. */
+/* The two middle order statistics of the histogram (ranks (k-1)/2 and k/2 of the k positive self-ligation distances it
+ * holds; -1 if k = 0, CLOOPS_ROUND_HIST_BINS if a rank lies in the overflow bin) and the round's moments on the host: h_mom =
+ * d_mom with the self-ligation entries completed from the histogram (h_mom[3] = k, h_mom[4], h_mom[5] += sum over bins of
+ * count * log2(bin) and count * log2(bin)^2, fixed summation order): what estIntSelCutFrag (cLoops/ests.py:36-61) needs.
+ * Synchronises the stream. */
 CLOOPS_API int cloops_round_middle(const int32_t* d_hist, const double* d_mom, int64_t* h_middle, double* h_mom, void* stream);
 CLOOPS_API int cloops_pass_run_host(const int32_t* h_x, const int32_t* h_y, int64_t n, int32_t eps, int32_t minPts, int32_t cut,
                          int32_t variant, int32_t score, cloops_pass** out, void* stream);
