@@ -501,6 +501,50 @@ __global__ void __launch_bounds__(256) v2_border_kernel(const u64* __restrict__ 
     if (!FIX && contested) W.list_con[atomicAdd(&W.counters[1], 1)] = i;
 }
 
+// The first ownership pass with G lanes per border point.  One lane per point walks its three strip ranges alone: the
+// lanes of a warp then read 32 unrelated places (ncu, chr1 of config 4: 9.5 sectors per load request, 14 of 32 lanes
+// active per instruction, 191 us).  Here the CTA's candidates are compacted and dealt to groups of G lanes; a group walks
+// one point's ranges with stride G and combines (lowest rank, contested) by shuffles inside the group.
+template <int G>
+__global__ void __launch_bounds__(256) v2_border_group_kernel(const u64* __restrict__ keys, const int* __restrict__ sstart,
+                                                              GridParams P, Work W, int n_items) {
+    __shared__ int q[256];
+    __shared__ int s_n;
+    const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
+    bool todo = i0 < n_items && !(keys[i0] >> 63);
+    if (todo) {
+        const u64 k0 = keys[i0];
+        todo = cb_any_core_near(W.corebits, (u32)(k0 >> P.sshift), ((u32)(k0 >> P.be) & P.umask) / (u32)P.eps);
+    }
+    const int n_todo = cta_compact(todo, q, &s_n);
+    const int lg = threadIdx.x % G;
+    const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << ((threadIdx.x & 31) / G * G);
+    for (int t = threadIdx.x / G; t < n_todo; t += 256 / G) {
+        const int i = blockIdx.x * blockDim.x + q[t];
+        const PointView p = view(keys[i], P);
+        int best_rank = INT_MAX, best_root = -1;
+        int contested = 0;
+        RootCache rc;
+        for_each_neighbour_strided<G>(keys, sstart, P, i, p, lg, [&](int j, u64 kq) {
+            if (!(kq >> 63)) return;
+            rc.lookup(W, j);
+            if (rc.status == ST_DEAD) return;
+            if (rc.status == ST_UNDECIDED) contested = 1;
+            if (rc.rank < best_rank) { best_rank = rc.rank; best_root = rc.root; }
+        });
+#pragma unroll
+        for (int d = G / 2; d > 0; d >>= 1) {
+            const int o_rank = __shfl_xor_sync(gmask, best_rank, d), o_root = __shfl_xor_sync(gmask, best_root, d);
+            contested |= __shfl_xor_sync(gmask, contested, d);
+            if (o_rank < best_rank) { best_rank = o_rank; best_root = o_root; }
+        }
+        if (lg == 0) {
+            W.assigned[i] = best_root;
+            if (contested) W.list_con[atomicAdd(&W.counters[1], 1)] = i;
+        }
+    }
+}
+
 // ---- numbering ----------------------------------------------------------------------------------------
 // flags[rank of root] = 1 for every component that receives an id
 __global__ void __launch_bounds__(256) number_flags_kernel(const u64* __restrict__ keys, GridParams P, Work W, int variant) {
@@ -610,7 +654,11 @@ int index_dbscan(cloops_index* ix, int minPts, int variant, int* d_labels, int* 
         stage_mark("border", st);
     } else {
         LAUNCH(v2_status_kernel, g, 256, 0, st, ix->keys, P, minPts, W);
-        LAUNCH(v2_border_kernel<false>, g, 256, 0, st, ix->keys, ix->sstart, P, W, na);
+        static const int border_group = getenv("CLOOPS_BORDER_GROUP") ? atoi(getenv("CLOOPS_BORDER_GROUP")) : 4;      // 1: one lane per point
+        if (border_group == 4) LAUNCH(v2_border_group_kernel<4>, g, 256, 0, st, ix->keys, ix->sstart, P, W, na);
+        else if (border_group == 8) LAUNCH(v2_border_group_kernel<8>, g, 256, 0, st, ix->keys, ix->sstart, P, W, na);
+        else if (border_group == 2) LAUNCH(v2_border_group_kernel<2>, g, 256, 0, st, ix->keys, ix->sstart, P, W, na);
+        else LAUNCH(v2_border_kernel<false>, g, 256, 0, st, ix->keys, ix->sstart, P, W, na);
         stage_mark("border", st);
         CU_TRY(cudaMemcpyAsync(counters, W.counters, sizeof(counters), cudaMemcpyDeviceToHost, st));
         CU_TRY(cudaStreamSynchronize(st));

@@ -93,6 +93,51 @@ __device__ __forceinline__ void for_each_neighbour(const u64* __restrict__ keys,
     }
 }
 
+// The same visit shared by G lanes: lane `lg` of the group takes every G-th candidate of each of the four ranges (the
+// candidates of a range are consecutive keys, so the G loads of a step fall into one or two sectors; the range ends are
+// monotone in the key, so every lane may stop on its own).  f(j, key_j); no early exit.
+template <int G, class F>
+__device__ __forceinline__ void for_each_neighbour_strided(const u64* __restrict__ keys, const int* __restrict__ sstart,
+                                                           const GridParams& P, int i, const PointView& p, int lg, F&& f) {
+    const int lo_s = sstart[p.s + 1], hi_s = sstart[p.s + 2];
+    for (int j = i - 1 - lg; j >= lo_s; j -= G) {
+        u64 kq = keys[j];
+        if (((u32)(kq >> P.be) & P.umask) < p.ulo) break;
+        f(j, kq);
+    }
+    for (int j = i + 1 + lg; j < hi_s; j += G) {
+        u64 kq = keys[j];
+        if ((u64)((u32)(kq >> P.be) & P.umask) > p.uhi) break;
+        f(j, kq);
+    }
+    {
+        const int a = sstart[p.s];
+        if (a < lo_s) {
+            u64 base = (u64)(p.s - 1) << P.bu;
+            int j = lower_bound_su(keys, a, lo_s, base | p.ulo, P.be) + lg;
+            u64 top = base | p.uhi;
+            for (; j < lo_s; j += G) {
+                u64 kq = keys[j];
+                if (key_su(kq, P.be) > top) break;
+                if (((u32)kq & P.emask) >= p.vm) f(j, kq);
+            }
+        }
+    }
+    {
+        const int b = sstart[p.s + 3];
+        if (hi_s < b) {
+            u64 base = (u64)(p.s + 1) << P.bu;
+            int j = lower_bound_su(keys, hi_s, b, base | p.ulo, P.be) + lg;
+            u64 top = base | p.uhi;
+            for (; j < b; j += G) {
+                u64 kq = keys[j];
+                if (key_su(kq, P.be) > top) break;
+                if (((u32)kq & P.emask) <= p.vm) f(j, kq);
+            }
+        }
+    }
+}
+
 int index_build(const int32_t* d_x, const int32_t* d_y, int64_t n, int32_t eps, int32_t cut, cloops_index** out,
                 cudaStream_t st);
 int index_filter(const cloops_index* base, int32_t cut, cloops_index** out, cudaStream_t st);
