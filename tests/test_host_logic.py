@@ -366,6 +366,27 @@ def test_native_ingest_equals_reference(tmp_path):
                 assert g.dtype == np.int64 and np.array_equal(np.asarray(w, dtype=np.int64), g)
 
 
+def test_native_ingest_of_the_bundled_example_equals_golden(gold_dir):
+    """The reference's only fixture (examples/*.bedpe.gz, copied to oracle/_ref/examples by oracle/make_ref.py so that it
+    travels to the GPU box) through cloops_bedpe_parse must give the committed golden coordinates, which oracle/make_golden.py
+    produced with the reference's own PET class (cLoops/io.py:30-59)."""
+    example = None
+    for root in (ref_shim.REF_ROOT, os.path.join(ROOT, "oracle", "_ref")):
+        f = os.path.join(root, "examples", "GSM1872886_GM12878_CTCF_ChIA-PET_chr21_hg38.bedpe.gz")
+        if os.path.isfile(f):
+            example = f
+            break
+    if example is None:
+        pytest.skip("the reference's example file is not available")
+    g = np.load(os.path.join(gold_dir, "chr21_pets.npz"))
+    order, per, ds = io.readBedpe([example], [], 0, logging.getLogger("t"))
+    assert order == ["chr21"] and ds is None
+    a, b = per["chr21"]
+    assert a.dtype == np.int64 and np.array_equal(a, g["X"]) and np.array_equal(b, g["Y"])
+    order, per, ds = io.readBedpe([example], [], 0, logging.getLogger("t"), dedup=True)
+    assert len(per["chr21"][0]) == len(g["X"]) and len(ds) > 0          # no duplicate (cA, cB) in the example (SURVEY 8c)
+
+
 def test_facade_argument_contract():
     """Errors that are part of the call surface and need no GPU: empty input (cDBSCAN2 -> {},
     v1/block -> IndexError as in cDBSCAN.py:77 / blockDBSCAN.py:74), malformed mat, non-integer eps."""
