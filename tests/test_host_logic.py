@@ -91,6 +91,58 @@ def test_removedup_and_marks_vs_live_reference():
             assert cModel.markIntSigHic(a.copy())["significant"].tolist() == ns.cModel.markIntSigHic(b.copy())["significant"].tolist()
 
 
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not mounted")
+def test_removedup_stress_ties_chains_vs_live_reference():
+    """cloops_remove_dup against the reference's removeDup (cModel.py:198-259, run live) where its order dependence shows:
+    anchors on a coarse lattice (long chains of overlapping loops, a member can overlap a group's leader but not its other
+    members), densities and p-values from small sets (shared maxima inside a group, p exactly at the cut-off), reversed
+    intervals (the sweep's precondition fails: pair-loop path), and the second pass over the survivors (cModel.py:318,322)."""
+    ns = ref_shim.load()
+    rng = np.random.default_rng(2024)
+    for trial in range(40):
+        n = int(rng.integers(2, 260))
+        step = int(rng.choice([50, 200, 1000]))
+        width = int(rng.choice([1, 2, 4])) * step
+        ds = {}
+        for k in range(n):
+            a0 = int(rng.integers(0, 40)) * step
+            a1 = a0 + int(rng.integers(0, 3)) * width // 2
+            b0 = a0 + int(rng.integers(2, 30)) * step
+            b1 = b0 + int(rng.integers(0, 3)) * width // 2
+            if trial % 8 == 7 and rng.random() < 0.1:
+                a0, a1 = a1, a0                                     # reversed interval
+            ra, rb = int(rng.choice([20, 40, 80])), int(rng.choice([20, 40, 80]))
+            ds["chr1-chr1-%d" % k] = {"iva": "chr1:%d-%d" % (a0, a1), "ivb": "chr1:%d-%d" % (b0, b1),
+                                      "rab": int(rng.choice([4, 8, 16])), "ra": ra, "rb": rb,
+                                      "binomial_p-value": float(rng.choice([1e-6, 1e-5, 2e-5, 1e-9])), "ES": 3.0, "FDR": 0.0,
+                                      "poisson_p-value": 1e-7, "hypergeometric_p-value": 1e-12}
+        got, want = cModel.removeDup(dict(ds)), ns.cModel.removeDup(dict(ds))
+        assert list(got.keys()) == list(want.keys()), trial
+        got2, want2 = cModel.removeDup(dict(got)), ns.cModel.removeDup(dict(want))
+        assert list(got2.keys()) == list(want2.keys()), trial
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not mounted")
+def test_combine_rounds_vs_live_reference():
+    """cloops_combine_rounds (all rounds of a chromosome in one hash pass) against the reference's combineTwice applied round
+    after round (cLoops/pipe.py:155-174, run live): boxes repeated inside one round stay (the known set is taken before the
+    round is appended), boxes seen in ANY earlier round go; order = round order, then position."""
+    ns = ref_shim.load()
+    rng = np.random.default_rng(77)
+    for trial in range(40):
+        n_rounds = int(rng.integers(1, 9))
+        pool = rng.integers(0, 50, (int(rng.integers(1, 40)), 4)).astype(np.int32) * np.int32(100)      # few distinct boxes: many repeats
+        rounds = [pool[rng.integers(0, len(pool), int(rng.integers(0, 30)))] for _ in range(n_rounds)]
+        rounds = [r for r in rounds if len(r)] or [pool[:1]]
+        got = pipe._combine_rounds([np.ascontiguousarray(r) for r in rounds])
+        dataI = {}
+        for r in rounds:
+            recs = [["c", int(b[0]), int(b[1]), "c", int(b[2]), int(b[3])] for b in r]
+            dataI = ns.pipe.combineTwice(dataI, {("c", "c"): {"f": "f", "records": recs}})
+        want = [[r[1], r[2], r[4], r[5]] for r in dataI[("c", "c")]["records"]]
+        assert got.tolist() == want, trial
+
+
 def test_table_from_counts_equals_reference_tail(gold):
     """The columnar statistics tail (tableFromCounts) against the reference's own tail (cModel.py:295-331: dict of dicts,
     removeDup twice, DataFrame(ds).T, Bonferroni) on the same counted integers: identical CSV text."""
